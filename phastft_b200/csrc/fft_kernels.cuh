@@ -1,0 +1,409 @@
+// fft_kernels.cuh -- the three sm_100a pass kernels of the B200 FFT.
+//
+// One launch = one "pass" over the whole signal: every CTA owns an R x C tile (R-point
+// sub-transform x C adjacent columns/rows), runs all log2(R) butterfly stages on it with
+// the tile held in shared memory between register-resident radix-4/8/16 stages, and
+// touches HBM exactly once for the read and once for the write.  A transform of
+// N = R_1 * R_2 [* R_3] points is 1, 2 or 3 such launches.
+//
+// What this replaces in the reference (all CPU, one sweep over memory per radix-2 stage):
+//   algorithms/dit.rs:33-164   recursive cache-blocked DIT driver      -> the pass decomposition
+//   algorithms/bravo.rs:82-251 BRAVO / CO-BRAVO bit-reversal           -> folded into addressing:
+//        digit-reversed placement into shared memory on load (stage 1) and the transposed
+//        store of the last pass; no separate permutation pass exists on the GPU
+//   kernels/dit.rs:971-1115    fft_dit_chunk_n (planner-twiddle stage) -> stage twiddles from the
+//        per-pass W_R table, inter-pass twiddles from a two-level W_N table built by the planner
+//   algorithms/dit.rs:325-331  inverse 1/N scaling loop                -> fused into the last store
+//
+// Kernel kinds
+//   KIND_COL   first / middle pass: tile rows are strided (stride B), columns contiguous.
+//              load [r][c] -> store [k][c], same addresses (layout preserving, in-place safe).
+//   KIND_TRANS last pass of a multi-pass plan: tile rows are contiguous sub-sequences, the C rows
+//              of a tile are C adjacent values of the slowest input digit; the store is the
+//              digit-reversing transpose, written as C-element contiguous runs.
+//   KIND_ROW   whole transform in one CTA (N <= 4096 f64 / 8192 f32): rows contiguous in and out.
+#pragma once
+
+#include "fft_device.cuh"
+
+namespace phast {
+
+enum { KIND_COL = 0, KIND_TRANS = 1, KIND_ROW = 2 };
+
+template <typename T>
+struct PassParams {
+    const T* in_re;                // planar input (or interleaved (re,im) pairs if in_interleaved)
+    const T* in_im;                // (no __restrict__: in-place passes alias in and out)
+    T* out_re;                     // planar output (or interleaved if out_interleaved)
+    T* out_im;
+    long long in_bstride;          // elements between consecutive transforms of the batch
+    long long out_bstride;
+    int batch;                     // number of transforms (KIND_ROW: may not be a multiple of C)
+    int in_interleaved;            // 1: in_re points at N (re,im) pairs (r2c first pass); 2: pairs, re/im swapped
+    int out_interleaved;           // 1: out_re points at N pairs; 2: pairs with re/im swapped (c2r)
+    // geometry
+    int log2A;                     // A = number of sub-transform groups before this digit
+    int log2B;                     // B = stride of this pass's digit = product of later pass sizes
+    int log2R1;                    // KIND_TRANS: size of the first pass digit (tile columns run over it)
+    int log2Rprev;                 // size of the previous pass digit (0 if no inter-pass twiddle)
+    int has_tw;                    // apply inter-pass twiddle on load
+    int tw_shift;                  // exponent scale: e_N = e_L << tw_shift   (N / L)
+    Tw2 tw2;                       // two-level W_N table
+    const cx<T>* __restrict__ tw_stage;  // W_R^e, e < R           (stage twiddles)
+    const cx<T>* __restrict__ tw_wc;     // KIND_TRANS, 2-pass plans: W_L^(c*m), [c][m] layout
+    T scale;                       // multiplied into the stored result (1/N for the inverse)
+};
+
+// Shared-memory tile addressing (units: complex elements).
+//   CFAST kernels (COL, TRANS): [pos][c'] with c' = c ^ swz(pos)  (swz == 0 for COL)
+//   ROW kernel: [c][pos'] with pos' = pos ^ swz(pos)
+// swz(pos) takes the bits of `pos` in which the low bits of the *memory-order* index of stage 1
+// land after digit reversal, so that the stage-1 scatter of a coalesced global read is
+// bank-conflict free; later stages address whole rows / aligned runs and are unaffected.
+template <class RL, int C, int KIND, typename T>
+struct TileAddr {
+    static constexpr int R = RL::R();
+    static constexpr int LOG2R = ilog2_c(R);
+    static constexpr int RS_LAST = RL::rad(RL::S - 1);
+    static constexpr int SWZ_SHIFT = LOG2R - ilog2_c(RS_LAST);
+    // 16-byte (f64) / 8-byte (f32) complex elements: a 128-byte wavefront holds 8 / 16 of them
+    static constexpr int LANES_PER_WF = 128 / (2 * (int)sizeof(T));
+    static constexpr int SWZ_MASK_WANT = LANES_PER_WF - 1;
+    static constexpr int SWZ_MASK_TRANS = (C - 1) < SWZ_MASK_WANT ? (C - 1) : SWZ_MASK_WANT;
+    static constexpr int SWZ_MASK_ROW = (R >= 4 * LANES_PER_WF) ? SWZ_MASK_WANT : 0;
+    static __device__ __forceinline__ int at(int pos, int c) {
+        if constexpr (KIND == KIND_COL) {
+            return pos * C + c;
+        } else if constexpr (KIND == KIND_TRANS) {
+            return pos * C + (c ^ ((pos >> SWZ_SHIFT) & SWZ_MASK_TRANS));
+        } else {
+            return c * R + (pos ^ ((pos >> SWZ_SHIFT) & SWZ_MASK_ROW));
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// The pass kernel.
+// ---------------------------------------------------------------------------------------------
+template <typename T, class RL, int C, int NT, int KIND>
+struct PassKernel {
+    static constexpr int S = RL::S;
+    static constexpr int R = RL::R();
+    static constexpr int LOG2R = ilog2_c(R);
+    static constexpr int R1 = RL::rad(0);          // first-stage radix
+    static constexpr int M = R / R1;               // stage-1 tasks per column
+    static constexpr int LOG2C = ilog2_c(C);
+    using Addr = TileAddr<RL, C, KIND, T>;
+    // shared memory: tile (only if S >= 2) + Um[M] + G[C][R1]
+    static constexpr int TILE_ELEMS = (S >= 2) ? R * C : 0;
+    static constexpr int G_ELEMS = (KIND == KIND_TRANS) ? C * R1 : R1;
+    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)(TILE_ELEMS + M + G_ELEMS);
+
+    // ---- global element access -------------------------------------------------------------
+    static __device__ __forceinline__ void gload(const PassParams<T>& p, long long idx, T& re, T& im) {
+        if (p.in_interleaved) {
+            cx<T> v = reinterpret_cast<const cx<T>*>(p.in_re)[idx];
+            if (p.in_interleaved == 1) { re = v.x; im = v.y; } else { re = v.y; im = v.x; }
+        } else {
+            re = p.in_re[idx];
+            im = p.in_im[idx];
+        }
+    }
+    static __device__ __forceinline__ void gstore(const PassParams<T>& p, long long idx, T re, T im) {
+        if (p.scale != T(1)) { re *= p.scale; im *= p.scale; }
+        if (p.out_interleaved == 0) {
+            p.out_re[idx] = re;
+            p.out_im[idx] = im;
+        } else if (p.out_interleaved == 1) {
+            reinterpret_cast<cx<T>*>(p.out_re)[idx] = make_cx<T>(re, im);
+        } else {
+            reinterpret_cast<cx<T>*>(p.out_re)[idx] = make_cx<T>(im, re);
+        }
+    }
+
+    // ---- one register-resident stage s >= 1 (0-based), reading from the tile ------------------
+    template <int s>
+    static __device__ __forceinline__ void stage_from_tile(const PassParams<T>& p, cx<T>* tile, long long out_base,
+                                                           long long out_kstride, int tile_rows_valid) {
+        constexpr int RAD = RL::rad(s);
+        constexpr int NS = RL::Ns(s);
+        constexpr int J = R / RAD;                      // tasks per column
+        constexpr int TW_SHIFT = LOG2R - ilog2_c(NS * RAD);
+        constexpr bool LAST = (s == S - 1);
+        constexpr int NTASK = J * C;
+#pragma unroll 1
+        for (int t = threadIdx.x; t < NTASK; t += NT) {
+            int c, j;
+            if constexpr (KIND == KIND_ROW) { j = t % J; c = t / J; } else { c = t % C; j = t / C; }
+            const int m = j & (NS - 1);
+            const int g = j / NS;
+            const int base = g * NS * RAD + m;
+            T xr[RAD], xi[RAD];
+#pragma unroll
+            for (int i = 0; i < RAD; ++i) {
+                cx<T> v = tile[Addr::at(base + i * NS, c)];
+                xr[i] = v.x; xi[i] = v.y;
+            }
+#pragma unroll
+            for (int i = 1; i < RAD; ++i) {
+                cx<T> w = __ldg(p.tw_stage + ((m * i) << TW_SHIFT));
+                T a = xr[i], b = xi[i];
+                xr[i] = fma_t(-b, w.y, a * w.x);
+                xi[i] = fma_t(b, w.x, a * w.y);
+            }
+            Dft<T, RAD>::run(xr, xi);
+            if constexpr (!LAST) {
+#pragma unroll
+                for (int k = 0; k < RAD; ++k) tile[Addr::at(base + k * NS, c)] = make_cx<T>(xr[k], xi[k]);
+            } else {
+                // last stage: g == 0, natural-order outputs kr = m + k*NS
+                if (KIND == KIND_ROW && c >= tile_rows_valid) continue;
+#pragma unroll
+                for (int k = 0; k < RAD; ++k) {
+                    long long idx;
+                    if constexpr (KIND == KIND_ROW) idx = out_base + (long long)c * p.out_bstride + (m + k * NS);
+                    else idx = out_base + (long long)(m + k * NS) * out_kstride + c;
+                    gstore(p, idx, xr[k], xi[k]);
+                }
+            }
+        }
+    }
+
+    template <int s>
+    static __device__ __forceinline__ void run_stages(const PassParams<T>& p, cx<T>* tile, long long out_base,
+                                                      long long out_kstride, int rows_valid) {
+        if constexpr (s < S) {
+            __syncthreads();
+            stage_from_tile<s>(p, tile, out_base, out_kstride, rows_valid);
+            run_stages<s + 1>(p, tile, out_base, out_kstride, rows_valid);
+        }
+    }
+
+    // ---- the kernel body ------------------------------------------------------------------------
+    static __device__ __forceinline__ void body(const PassParams<T>& p) {
+        extern __shared__ __align__(16) unsigned char smem_raw[];
+        cx<T>* tile = reinterpret_cast<cx<T>*>(smem_raw);
+        cx<T>* s_um = tile + TILE_ELEMS;   // [M]       per-CTA  W_L^(kp*B*m')
+        cx<T>* s_g = s_um + M;             // [C][R1] or [R1]     W_L^(kp(c)*M*B*i)
+
+        const int tid = threadIdx.x;
+        long long in_base, out_base, out_kstride;
+        long long in_rstride;          // element stride of the tile row index r (COL) / 1 (ROW, TRANS)
+        long long in_cstride;          // element stride between tile columns
+        int rows_valid = C;
+        uint32_t kp0 = 0;              // previous-pass output digit of column c = 0
+        uint32_t kp_cstep = 0;         // ... and its increment per column
+        uint32_t bcol0 = 0;            // flat index of the remaining digits for column 0 (COL only)
+
+        if constexpr (KIND == KIND_COL) {
+            const int tilesB = 1 << (p.log2B - LOG2C);
+            const int bt = blockIdx.x & (tilesB - 1);
+            const int rest = blockIdx.x >> (p.log2B - LOG2C);
+            const int a = rest & ((1 << p.log2A) - 1);
+            const int batch = rest >> p.log2A;
+            const long long off = ((long long)a << (LOG2R + p.log2B)) + ((long long)bt << LOG2C);
+            in_base = (long long)batch * p.in_bstride + off;
+            out_base = (long long)batch * p.out_bstride + off;
+            in_rstride = 1LL << p.log2B;
+            in_cstride = 1;
+            out_kstride = in_rstride;
+            kp0 = a & ((1u << p.log2Rprev) - 1u);
+            bcol0 = (uint32_t)bt << LOG2C;
+        } else if constexpr (KIND == KIND_TRANS) {
+            // rows of the tile: a(c) = (k0 + c) * rest_n + rest, rest_n = A / R1
+            const int log2restn = p.log2A - p.log2R1;
+            const int tilesK = 1 << (p.log2R1 - LOG2C);
+            const int kt = blockIdx.x & (tilesK - 1);
+            const int tmp = blockIdx.x >> (p.log2R1 - LOG2C);
+            const int rest = tmp & ((1 << log2restn) - 1);
+            const int batch = tmp >> log2restn;
+            const int k0 = kt << LOG2C;
+            in_base = (long long)batch * p.in_bstride + ((((long long)k0 << log2restn) + rest) << LOG2R);
+            in_rstride = 1;
+            in_cstride = 1LL << (log2restn + LOG2R);
+            // out[(k0 + c) + R1*rest + A*kr]
+            out_base = (long long)batch * p.out_bstride + k0 + ((long long)rest << p.log2R1);
+            out_kstride = 1LL << p.log2A;
+            const uint32_t rprev_mask = (1u << p.log2Rprev) - 1u;
+            kp0 = (uint32_t)(((long long)k0 << log2restn) + rest) & rprev_mask;
+            kp_cstep = (log2restn == 0) ? 1u : 0u;   // 2-pass plan: kp = k1 = k0 + c ; 3-pass: kp = k2
+        } else {
+            const long long first = (long long)blockIdx.x * C;
+            rows_valid = (int)min((long long)C, (long long)p.batch - first);
+            in_base = first * p.in_bstride;
+            out_base = first * p.out_bstride;
+            in_rstride = 1;
+            in_cstride = p.in_bstride;
+            out_kstride = 1;
+        }
+
+        // ---- per-CTA inter-pass twiddle factors (two-level lookups, f64, once per CTA) ----------
+        // tw(r, c) = W_L^( kp(c) * (r*B + bcol(c)) ),  r = m' + i*M
+        //          = W_L^(kp*B*m') * W_L^(kp*bcol) * W_L^(kp*M*B*i)  =  Um[m'] * V[c] * G[c][i]
+        cx<T> vreg = make_cx<T>(T(1), T(0));
+        const bool has_tw = (KIND != KIND_ROW) && p.has_tw;
+        if (has_tw) {
+            const int log2B = (KIND == KIND_COL) ? p.log2B : 0;
+            for (int mp = tid; mp < M; mp += NT) {
+                uint32_t e = (kp0 * (uint32_t)mp) << log2B;
+                s_um[mp] = to_cx<T>(p.tw2.get(e << p.tw_shift));
+            }
+            constexpr int LOG2M = ilog2_c(M);
+            for (int q = tid; q < G_ELEMS; q += NT) {
+                const int i = q % R1;
+                const int c = q / R1;
+                uint32_t kp = kp0 + kp_cstep * (uint32_t)c;
+                uint32_t e = (kp * (uint32_t)i) << (LOG2M + log2B);
+                s_g[q] = to_cx<T>(p.tw2.get(e << p.tw_shift));
+            }
+            if constexpr (KIND == KIND_COL) {
+                const int c = tid % C;   // NT % C == 0: a thread keeps its column for the whole kernel
+                uint32_t e = kp0 * (bcol0 + (uint32_t)c);
+                vreg = to_cx<T>(p.tw2.get(e << p.tw_shift));
+            }
+            __syncthreads();
+        }
+
+        // ---- stage 1: global -> registers -> (twiddle, DFT) -> tile (or global when S == 1) ------
+        {
+            constexpr int NTASK = M * C;
+#pragma unroll 1
+            for (int t = tid; t < NTASK; t += NT) {
+                int c, mp;
+                if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
+                T xr[R1], xi[R1];
+                const bool valid = (KIND != KIND_ROW) || (c < rows_valid);
+                if (valid) {
+                    const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) gload(p, a0 + (long long)(i * M) * in_rstride, xr[i], xi[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) { xr[i] = T(0); xi[i] = T(0); }
+                }
+                if (has_tw) {
+                    cx<T> pt = s_um[mp];
+                    if constexpr (KIND == KIND_COL) {
+                        pt = cmul<T>(pt, vreg);
+                    } else {
+                        if (kp_cstep) pt = cmul<T>(pt, __ldg(p.tw_wc + c * M + mp));
+                    }
+                    const cx<T>* g = (KIND == KIND_TRANS) ? (s_g + c * R1) : s_g;
+                    {
+                        T a = xr[0], b = xi[0];
+                        xr[0] = fma_t(-b, pt.y, a * pt.x);
+                        xi[0] = fma_t(b, pt.x, a * pt.y);
+                    }
+#pragma unroll
+                    for (int i = 1; i < R1; ++i) {
+                        cx<T> w = cmul<T>(pt, g[i]);
+                        T a = xr[i], b = xi[i];
+                        xr[i] = fma_t(-b, w.y, a * w.x);
+                        xi[i] = fma_t(b, w.x, a * w.y);
+                    }
+                }
+                Dft<T, R1>::run(xr, xi);
+                if constexpr (S >= 2) {
+                    const int j = rev_tail<RL>(mp);
+#pragma unroll
+                    for (int k = 0; k < R1; ++k) tile[Addr::at(j * R1 + k, c)] = make_cx<T>(xr[k], xi[k]);
+                } else {
+                    if (valid) {
+#pragma unroll
+                        for (int k = 0; k < R1; ++k) {
+                            long long idx;
+                            if constexpr (KIND == KIND_ROW) idx = out_base + (long long)c * p.out_bstride + k;
+                            else idx = out_base + (long long)k * out_kstride + c;
+                            gstore(p, idx, xr[k], xi[k]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- stages 2..S -------------------------------------------------------------------------
+        run_stages<1>(p, tile, out_base, out_kstride, rows_valid);
+    }
+};
+
+template <typename T, class RL, int C, int NT, int KIND>
+__global__ void __launch_bounds__(NT) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {
+    PassKernel<T, RL, C, NT, KIND>::body(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// r2c post-processing (reference: simd_untangle_inplace_*, algorithms/r2c.rs:150-242) and c2r
+// pre-processing (simd_c2r_preprocess_*, r2c.rs:263-432).  Elementwise over bin pairs (k, half-k).
+// The planner's w[k] = 0.5 * W_N^k table (planner.rs:120-162, an O(N) rotation recurrence on the
+// CPU) is replaced by a two-level lookup: consecutive k hit consecutive `lo` entries (coalesced)
+// and one broadcast `hi` entry.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct RealParams {
+    T* __restrict__ re;         // untangle: in/out (length half+1).  preprocess: z_re out (length half)
+    T* __restrict__ im;
+    const T* __restrict__ in_re;  // preprocess only: spectrum (length half+1)
+    const T* __restrict__ in_im;
+    long long bstride;          // elements between batch members in re/im
+    long long in_bstride;
+    int log2half;
+    Tw2 tw2;                    // two-level table for W_N, N = 2*half
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) r2c_untangle_kernel(const __grid_constant__ RealParams<T> p) {
+    const long long half = 1LL << p.log2half;
+    const long long q = half >> 1;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    T* re = p.re + (long long)blockIdx.y * p.bstride;
+    T* im = p.im + (long long)blockIdx.y * p.bstride;
+    if (k > q) return;
+    if (k == 0) {
+        // r2c.rs:161-166
+        T a0 = re[0], b0 = im[0];
+        re[0] = a0 + b0; im[0] = T(0);
+        re[half] = a0 - b0; im[half] = T(0);
+        return;
+    }
+    double2 wd = p.tw2.get((uint32_t)k);
+    const T wkr = T(0.5 * wd.x), wki = T(0.5 * wd.y);
+    if (k == q) {
+        // r2c.rs:233-236 (self pair)
+        T a = re[q], b = im[q];
+        re[q] = a + T(2) * wkr * b;
+        im[q] = T(2) * wki * b;
+        return;
+    }
+    const long long m = half - k;
+    T a = re[k], b = im[k], c = re[m], d = im[m];
+    T s_re = T(0.5) * (a + c), s_im = T(0.5) * (b - d);
+    T t_re = b + d, t_im = c - a;
+    T wzr = wkr * t_re - wki * t_im;
+    T wzi = wkr * t_im + wki * t_re;
+    re[k] = s_re + wzr; im[k] = s_im + wzi;
+    re[m] = s_re - wzr; im[m] = wzi - s_im;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) c2r_preprocess_kernel(const __grid_constant__ RealParams<T> p) {
+    const long long half = 1LL << p.log2half;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= half) return;
+    const T* ire = p.in_re + (long long)blockIdx.y * p.in_bstride;
+    const T* iim = p.in_im + (long long)blockIdx.y * p.in_bstride;
+    T* zre = p.re + (long long)blockIdx.y * p.bstride;
+    T* zim = p.im + (long long)blockIdx.y * p.bstride;
+    const long long m = half - k;
+    double2 wd = p.tw2.get((uint32_t)k);
+    const T c_h = T(0.5 * wd.x), s_h = T(0.5 * wd.y);
+    // r2c.rs:263-347
+    T re_f = ire[k], im_f = iim[k];
+    T re_s = ire[m], im_s = -iim[m];
+    T zx_re = T(0.5) * (re_f + re_s), zx_im = T(0.5) * (im_f + im_s);
+    T dr = re_f - re_s, di = im_f - im_s;
+    T zy_re = c_h * dr + s_h * di;
+    T zy_im = c_h * di - s_h * dr;
+    zre[k] = zx_re - zy_im;
+    zim[k] = zx_im + zy_re;
+}
+
+}  // namespace phast

@@ -1,0 +1,1028 @@
+// phastft_cuda.cu -- planner, launcher and C ABI of libphastft_cuda.so (see include/phastft_cuda.h).
+//
+// Reference items replaced (QuState/PhastFT @ 8cd3a39, paths under /root/reference/src):
+//   planner.rs:34-114   PlannerDit{64,32}: per-stage cos/sin tables, total 2(N-64) entries
+//        -> Plan<T>: pass decomposition N = R_1*R_2[*R_3], a two-level W_N table (2*sqrt(N)
+//           f64 entries) for the inter-pass twiddles and one W_R table per pass
+//   planner.rs:164-212  PlannerR2c{64,32}                      -> PlanR2c<T>
+//   algorithms/dit.rs:263-401 fft_*_dit_with_planner_and_opts  -> run_c2c(): 1-3 kernel launches
+//   algorithms/r2c.rs:521-895 r2c / c2r entry points            -> r2c_dev() / c2r_dev()
+//   options.rs:10-43    Options                                 -> accepted, no effect on the GPU
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/phastft_cuda.h"
+#include "fft_kernels.cuh"
+
+using namespace phast;
+
+// =================================================================================================
+// errors
+// =================================================================================================
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<uint64_t> g_launches{0};
+
+int32_t fail(int32_t code, const std::string& detail = std::string()) {
+    g_last_error = phastft_status_message(code);
+    if (!detail.empty()) { g_last_error += ": "; g_last_error += detail; }
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) {                                                                        \
+            int32_t _code = (_e == cudaErrorNoDevice || _e == cudaErrorInsufficientDriver ||            \
+                             _e == cudaErrorInvalidDevice)                                              \
+                                ? PHASTFT_ERR_NO_DEVICE                                                 \
+                                : PHASTFT_ERR_CUDA;                                                     \
+            return fail(_code, std::string(#expr) + " -> " + cudaGetErrorString(_e));                   \
+        }                                                                                               \
+    } while (0)
+
+inline bool is_pow2(size_t n) { return n != 0 && (n & (n - 1)) == 0; }
+inline int ilog2(size_t n) { int l = 0; while (n >>= 1) ++l; return l; }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// =================================================================================================
+// kernel registry
+// =================================================================================================
+template <typename T>
+struct KernelEntry {
+    int kind, R, C, NT, first_radix, stages;
+    size_t smem;
+    const void* fn;
+    std::string radices;
+};
+
+template <typename T, int KIND, int C, int NT, int... Rs>
+KernelEntry<T> make_entry() {
+    using RL = RadixList<Rs...>;
+    using PK = PassKernel<T, RL, C, NT, KIND>;
+    static_assert(NT % 32 == 0, "whole warps");
+    static_assert(KIND != KIND_COL || NT % C == 0, "a COL thread keeps its column");
+    static_assert(PK::SMEM_BYTES <= 227 * 1024, "tile exceeds the 227 KB shared memory of an sm_100 CTA");
+    KernelEntry<T> e;
+    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S;
+    e.smem = PK::SMEM_BYTES;
+    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND>);
+    const int rs[] = {Rs...};
+    for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
+    return e;
+}
+
+// Tile width in columns for the strided (HBM-facing) kinds: C * sizeof(T) = 64 B (CN) or 128 B (CW).
+template <typename T> struct TileC;
+template <> struct TileC<double> { static constexpr int CN = 8, CW = 16; };
+template <> struct TileC<float> { static constexpr int CN = 16, CW = 32; };
+
+template <typename T>
+const std::vector<KernelEntry<T>>& registry() {
+    static const std::vector<KernelEntry<T>> reg = [] {
+        std::vector<KernelEntry<T>> v;
+        constexpr int CN = TileC<T>::CN, CW = TileC<T>::CW;
+        // ---- whole transform in one CTA (rows contiguous in and out) -------------------------------
+        v.push_back(make_entry<T, KIND_ROW, 64, 64, 2>());
+        v.push_back(make_entry<T, KIND_ROW, 64, 64, 4>());
+        v.push_back(make_entry<T, KIND_ROW, 64, 64, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 32, 32, 16>());
+        v.push_back(make_entry<T, KIND_ROW, 16, 64, 4, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 8, 64, 8, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 4, 64, 16, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 2, 64, 4, 8, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 1, 64, 8, 8, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 1, 128, 16, 8, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 1, 256, 4, 8, 8, 8>());
+        v.push_back(make_entry<T, KIND_ROW, 1, 256, 8, 8, 8, 8>());
+        if constexpr (sizeof(T) == 4) v.push_back(make_entry<T, KIND_ROW, 1, 512, 16, 8, 8, 8>());
+        // ---- first / middle passes (strided rows, contiguous C-element runs) -----------------------
+        v.push_back(make_entry<T, KIND_COL, CN, 32, 4, 8>());
+        v.push_back(make_entry<T, KIND_COL, CN, 64, 8, 8>());
+        v.push_back(make_entry<T, KIND_COL, CN, 128, 16, 8>());
+        v.push_back(make_entry<T, KIND_COL, CN, 256, 4, 8, 8>());
+        v.push_back(make_entry<T, KIND_COL, CN, 256, 8, 8, 8>());
+        v.push_back(make_entry<T, KIND_COL, CN, 256, 16, 8, 8>());
+        v.push_back(make_entry<T, KIND_COL, CW, 64, 4, 8>());
+        v.push_back(make_entry<T, KIND_COL, CW, 128, 8, 8>());
+        v.push_back(make_entry<T, KIND_COL, CW, 256, 16, 8>());
+        v.push_back(make_entry<T, KIND_COL, CW, 256, 4, 8, 8>());
+        v.push_back(make_entry<T, KIND_COL, CW, 256, 8, 8, 8>());
+        // ---- last pass of a multi-pass plan (contiguous rows in, transposed C-runs out) -------------
+        v.push_back(make_entry<T, KIND_TRANS, CN, 32, 4, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CN, 64, 8, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CN, 128, 16, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CN, 256, 4, 8, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CN, 256, 8, 8, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CN, 256, 16, 8, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CW, 64, 4, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CW, 128, 8, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CW, 256, 16, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CW, 256, 4, 8, 8>());
+        v.push_back(make_entry<T, KIND_TRANS, CW, 256, 8, 8, 8>());
+        return v;
+    }();
+    return reg;
+}
+
+const char* kind_name(int k) { return k == KIND_COL ? "COL" : k == KIND_TRANS ? "TRANS" : "ROW"; }
+
+// =================================================================================================
+// twiddle generation (host, extended precision, octant-reduced so symmetric entries are exact)
+// =================================================================================================
+void root_of_unity(uint64_t k, uint64_t n, double& re, double& im) {
+    // W_n^k = exp(-2*pi*i*k/n), n a power of two
+    k &= (n - 1);
+    if (n < 8) {
+        // n in {1, 2, 4}
+        static const double c4[4] = {1, 0, -1, 0}, s4[4] = {0, -1, 0, 1};
+        uint64_t q = k * (4 / n);
+        re = c4[q]; im = s4[q];
+        return;
+    }
+    const uint64_t eighth = n / 8;
+    const uint64_t oct = k / eighth, rem = k % eighth;
+    auto cs = [&](uint64_t j, long double& c, long double& s) {
+        if (j == 0) { c = 1.0L; s = 0.0L; return; }
+        if (j == eighth) { c = s = 0.70710678118654752440084436210484903928L; return; }
+        long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)n;
+        c = cosl(a); s = sinl(a);
+    };
+    long double c, s, co, si;
+    switch (oct) {
+        case 0: cs(rem, c, s); co = c; si = s; break;
+        case 1: cs(eighth - rem, c, s); co = s; si = c; break;
+        case 2: cs(rem, c, s); co = -s; si = c; break;
+        case 3: cs(eighth - rem, c, s); co = -c; si = s; break;
+        case 4: cs(rem, c, s); co = -c; si = -s; break;
+        case 5: cs(eighth - rem, c, s); co = -s; si = -c; break;
+        case 6: cs(rem, c, s); co = s; si = -c; break;
+        default: cs(eighth - rem, c, s); co = c; si = -s; break;
+    }
+    re = (double)co;
+    im = (double)(-si);
+    if (re == 0.0) re = 0.0;
+    if (im == 0.0) im = 0.0;
+}
+
+// =================================================================================================
+// plans
+// =================================================================================================
+constexpr int MAX_PASSES = 3;
+
+template <typename T>
+struct PassDesc {
+    const KernelEntry<T>* k = nullptr;
+    int log2R = 0, log2A = 0, log2B = 0, log2R1 = 0, log2Rprev = 0, has_tw = 0, tw_shift = 0;
+    size_t tw_stage_off = 0;  // byte offsets into the table blob
+    size_t tw_wc_off = (size_t)-1;
+};
+
+template <typename T>
+struct Plan {
+    size_t n = 0;
+    int log2n = 0;
+    int device = 0;
+    int num_passes = 0;
+    PassDesc<T> pass[MAX_PASSES];
+    // table blob: [tw2_hi][tw2_lo][per pass W_R][wc]
+    std::vector<unsigned char> blob_host;
+    unsigned char* blob_dev = nullptr;
+    size_t hi_off = 0, lo_off = 0;
+    int lo_bits = 0;
+    // workspace (multi-pass only) and host-API staging, grown lazily under `mu`
+    mutable std::mutex mu;
+    mutable T* ws_re = nullptr;
+    mutable T* ws_im = nullptr;
+    mutable size_t ws_elems = 0;        // per array
+    mutable T* stage_re = nullptr;      // host-API staging (N each, or 2N for interleaved in stage_re)
+    mutable T* stage_im = nullptr;
+    mutable size_t stage_elems = 0;
+    mutable cudaStream_t stream = nullptr;   // used by the *_host entry points
+    mutable cudaEvent_t ws_free = nullptr;   // orders workspace reuse across streams
+    mutable cudaStream_t ws_last_stream = nullptr;
+    mutable bool ws_used = false;
+    std::string description;
+
+    ~Plan() {
+        DeviceGuard g(device);
+        if (blob_dev) cudaFree(blob_dev);
+        if (ws_re) cudaFree(ws_re);
+        if (ws_im) cudaFree(ws_im);
+        if (stage_re) cudaFree(stage_re);
+        if (stage_im) cudaFree(stage_im);
+        if (ws_free) cudaEventDestroy(ws_free);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+// pass sizes (log2) for a transform of 2^n points -------------------------------------------------
+template <typename T>
+std::vector<int> choose_factors(int n) {
+    // override: PHASTFT_FACTORS="20:10,10;26:9,9,8"  (applies to both precisions; tuning aid)
+    if (const char* env = getenv("PHASTFT_FACTORS")) {
+        std::string s(env);
+        size_t pos = 0;
+        while (pos < s.size()) {
+            size_t end = s.find(';', pos);
+            if (end == std::string::npos) end = s.size();
+            std::string item = s.substr(pos, end - pos);
+            size_t colon = item.find(':');
+            if (colon != std::string::npos && atoi(item.substr(0, colon).c_str()) == n) {
+                std::vector<int> f;
+                int sum = 0;
+                size_t p = colon + 1;
+                while (p < item.size()) {
+                    size_t q = item.find(',', p);
+                    if (q == std::string::npos) q = item.size();
+                    f.push_back(atoi(item.substr(p, q - p).c_str()));
+                    sum += f.back();
+                    p = q + 1;
+                }
+                if (sum == n && !f.empty() && (int)f.size() <= MAX_PASSES) return f;
+            }
+            pos = end + 1;
+        }
+    }
+    const int single_max = sizeof(T) == 8 ? 12 : 13;
+    if (n <= single_max) return {n};
+    if (n <= 20) { int a = (n + 1) / 2; return {a, n - a}; }
+    int a = (n + 2) / 3, b = (n - a + 1) / 2;
+    return {a, b, n - a - b};
+}
+
+template <typename T>
+const KernelEntry<T>* pick_kernel(int kind, int R, int max_c) {
+    int want_c = 0;
+    if (const char* env = getenv("PHASTFT_TILE_C")) want_c = atoi(env);
+    const KernelEntry<T>* best = nullptr;
+    for (const auto& e : registry<T>()) {
+        if (e.kind != kind || e.R != R) continue;
+        if (kind != KIND_ROW && e.C > max_c) continue;
+        if (!best) best = &e;
+        if (want_c && e.C == want_c) { best = &e; break; }
+    }
+    return best;
+}
+
+template <typename T>
+int32_t build_plan(size_t n, int device, Plan<T>** out) {
+    if (!out) return fail(PHASTFT_ERR_INVALID_ARG, "out == NULL");
+    *out = nullptr;
+    if (!is_pow2(n)) return fail(PHASTFT_ERR_NOT_POW2);          // planner.rs:66
+    if (n > (size_t(1) << 30)) return fail(PHASTFT_ERR_INVALID_ARG, "num_points > 2^30 not supported");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) return fail(PHASTFT_ERR_NO_DEVICE, ce != cudaSuccess ? cudaGetErrorString(ce) : "");
+    if (device < 0 || device >= count) return fail(PHASTFT_ERR_NO_DEVICE, "device ordinal out of range");
+    DeviceGuard guard(device);
+
+    std::unique_ptr<Plan<T>> pl(new Plan<T>());
+    pl->n = n;
+    pl->log2n = ilog2(n);
+    pl->device = device;
+    const int ln = pl->log2n;
+
+    std::vector<int> f = ln == 0 ? std::vector<int>{} : choose_factors<T>(ln);
+    pl->num_passes = (int)f.size();
+    // two-level W_N table
+    pl->lo_bits = (ln + 1) / 2;
+    const size_t n_lo = size_t(1) << pl->lo_bits, n_hi = size_t(1) << (ln - pl->lo_bits);
+    size_t off = 0;
+    pl->hi_off = off; off += n_hi * sizeof(double2);
+    pl->lo_off = off; off += n_lo * sizeof(double2);
+
+    int acc = 0;
+    for (int p = 0; p < pl->num_passes; ++p) {
+        PassDesc<T>& d = pl->pass[p];
+        d.log2R = f[p];
+        d.log2A = acc;
+        d.log2B = ln - acc - f[p];
+        d.log2R1 = f[0];
+        acc += f[p];
+        const bool last = (p == pl->num_passes - 1);
+        const int kind = pl->num_passes == 1 ? KIND_ROW : (last ? KIND_TRANS : KIND_COL);
+        const int max_c = kind == KIND_COL ? (1 << d.log2B) : kind == KIND_TRANS ? (1 << f[0]) : (1 << 30);
+        d.k = pick_kernel<T>(kind, 1 << f[p], max_c);
+        if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
+        if (p > 0) {
+            d.has_tw = 1;
+            d.log2Rprev = f[p - 1];
+            d.tw_shift = ln - (f[p - 1] + f[p] + d.log2B);
+        }
+        d.tw_stage_off = off; off += (size_t(1) << f[p]) * sizeof(cx<T>);
+        if (kind == KIND_TRANS && pl->num_passes == 2) {
+            d.tw_wc_off = off;
+            off += (size_t)d.k->C * ((size_t(1) << f[p]) / d.k->first_radix) * sizeof(cx<T>);
+        }
+        off = (off + 255) & ~size_t(255);
+    }
+    // ---- fill the blob ------------------------------------------------------------------------------
+    pl->blob_host.assign(off ? off : 256, 0);
+    {
+        double2* hi = reinterpret_cast<double2*>(pl->blob_host.data() + pl->hi_off);
+        double2* lo = reinterpret_cast<double2*>(pl->blob_host.data() + pl->lo_off);
+        for (size_t h = 0; h < n_hi; ++h) root_of_unity((uint64_t)h << pl->lo_bits, n, hi[h].x, hi[h].y);
+        for (size_t l = 0; l < n_lo; ++l) root_of_unity(l, n, lo[l].x, lo[l].y);
+    }
+    for (int p = 0; p < pl->num_passes; ++p) {
+        PassDesc<T>& d = pl->pass[p];
+        const size_t R = size_t(1) << d.log2R;
+        cx<T>* tw = reinterpret_cast<cx<T>*>(pl->blob_host.data() + d.tw_stage_off);
+        for (size_t e = 0; e < R; ++e) {
+            double re, im;
+            root_of_unity(e, R, re, im);
+            tw[e].x = (T)re; tw[e].y = (T)im;
+        }
+        if (d.tw_wc_off != (size_t)-1) {
+            // W_L^(c*m), L = N (2-pass plan), [c][m] layout, m < M = R / first_radix
+            const size_t M = R / d.k->first_radix;
+            cx<T>* wc = reinterpret_cast<cx<T>*>(pl->blob_host.data() + d.tw_wc_off);
+            for (int c = 0; c < d.k->C; ++c)
+                for (size_t m = 0; m < M; ++m) {
+                    double re, im;
+                    root_of_unity((uint64_t)c * m, n, re, im);
+                    wc[(size_t)c * M + m].x = (T)re; wc[(size_t)c * M + m].y = (T)im;
+                }
+        }
+    }
+    CUDA_TRY(cudaMalloc(&pl->blob_dev, pl->blob_host.size()));
+    CUDA_TRY(cudaMemcpy(pl->blob_dev, pl->blob_host.data(), pl->blob_host.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&pl->ws_free, cudaEventDisableTiming));
+    for (int p = 0; p < pl->num_passes; ++p)
+        CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].k->smem));
+    if (pl->num_passes >= 2) {
+        CUDA_TRY(cudaMalloc(&pl->ws_re, n * sizeof(T)));
+        CUDA_TRY(cudaMalloc(&pl->ws_im, n * sizeof(T)));
+        pl->ws_elems = n;
+    }
+    // description
+    {
+        std::string s = "n=2^" + std::to_string(ln) + (sizeof(T) == 8 ? " f64:" : " f32:");
+        if (pl->num_passes == 0) s += " identity";
+        for (int p = 0; p < pl->num_passes; ++p) {
+            const auto* k = pl->pass[p].k;
+            s += std::string(p ? " |" : "") + " " + kind_name(k->kind) + " R=" + std::to_string(k->R) + "(" + k->radices + ") C=" +
+                 std::to_string(k->C) + " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
+        }
+        pl->description = s;
+    }
+    *out = pl.release();
+    return PHASTFT_OK;
+}
+
+// =================================================================================================
+// execution
+// =================================================================================================
+template <typename T>
+struct Io {
+    const T* in_re; const T* in_im;
+    T* out_re; T* out_im;
+    long long in_bstride, out_bstride;
+    int in_il, out_il;   // 0 planar, 1 interleaved, 2 interleaved with re/im swapped
+};
+
+template <typename T>
+int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, cudaStream_t stream) {
+    const PassDesc<T>& d = pl.pass[p];
+    const KernelEntry<T>* k = d.k;
+    PassParams<T> prm = base;
+    prm.batch = (int)batch;
+    prm.log2A = d.log2A; prm.log2B = d.log2B; prm.log2R1 = d.log2R1; prm.log2Rprev = d.log2Rprev;
+    prm.has_tw = d.has_tw; prm.tw_shift = d.tw_shift;
+    prm.tw2.hi = reinterpret_cast<const double2*>(pl.blob_dev + pl.hi_off);
+    prm.tw2.lo = reinterpret_cast<const double2*>(pl.blob_dev + pl.lo_off);
+    prm.tw2.lo_bits = pl.lo_bits;
+    prm.tw_stage = reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_stage_off);
+    prm.tw_wc = d.tw_wc_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_wc_off);
+    unsigned long long blocks;
+    if (k->kind == KIND_ROW) blocks = (batch + k->C - 1) / k->C;
+    else blocks = (unsigned long long)batch * (pl.n >> d.log2R) / k->C;
+    if (blocks == 0 || blocks > 0x7fffffffULL) return fail(PHASTFT_ERR_INVALID_ARG, "grid too large");
+    void* args[] = {&prm};
+    CUDA_TRY(cudaLaunchKernel(k->fn, dim3((unsigned)blocks), dim3(k->NT), args, k->smem, stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PHASTFT_OK;
+}
+
+// Bytes of intermediate (workspace) data we try to keep L2-resident when a batch is processed in
+// chunks: pass p writes the chunk's intermediate, pass p+1 reads it back before it is evicted.
+constexpr size_t L2_CHUNK_BYTES = 48u << 20;
+
+// `pass_events` (profiling aid, bench.py roofline): if non-NULL, num_passes+1 events are recorded
+// around the passes of the FIRST chunk.
+template <typename T>
+int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaStream_t stream,
+                cudaEvent_t* pass_events = nullptr) {
+    if (batch == 0) return PHASTFT_OK;
+    PassParams<T> prm;
+    memset(&prm, 0, sizeof(prm));
+    if (pl.num_passes == 0) {
+        // N == 1: the transform is the identity (the reference runs zero stages, dit.rs:44-65).
+        if (io.in_re != io.out_re || io.in_il != io.out_il || scale != T(1))
+            return fail(PHASTFT_ERR_INVALID_ARG, "N == 1 supports only the in-place unscaled form");
+        return PHASTFT_OK;
+    }
+    if (pl.num_passes == 1) {
+        size_t done = 0;
+        const size_t max_chunk = (size_t)1 << 24;
+        while (done < batch) {
+            size_t nb = std::min(batch - done, max_chunk);
+            prm.in_re = io.in_re + (io.in_il ? 2 : 1) * done * io.in_bstride;
+            prm.in_im = io.in_im ? io.in_im + done * io.in_bstride : nullptr;
+            prm.out_re = io.out_re + (io.out_il ? 2 : 1) * done * io.out_bstride;
+            prm.out_im = io.out_im ? io.out_im + done * io.out_bstride : nullptr;
+            prm.in_bstride = io.in_bstride; prm.out_bstride = io.out_bstride;
+            prm.in_interleaved = io.in_il; prm.out_interleaved = io.out_il;
+            prm.scale = scale;
+            if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
+            int32_t st = launch_pass(pl, 0, prm, nb, stream);
+            if (st) return st;
+            if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[1], stream));
+            done += nb;
+        }
+        return PHASTFT_OK;
+    }
+    // multi-pass: in -> ws (COL) [-> ws (COL)] -> out (TRANS), batch processed in L2-sized chunks
+    std::lock_guard<std::mutex> lock(pl.mu);
+    const size_t bytes_per = pl.n * 2 * sizeof(T);
+    size_t chunk = std::max<size_t>(1, L2_CHUNK_BYTES / bytes_per);
+    chunk = std::min(chunk, batch);
+    if (pl.ws_elems < chunk * pl.n) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (pl.ws_re) cudaFree(pl.ws_re);
+        if (pl.ws_im) cudaFree(pl.ws_im);
+        pl.ws_re = pl.ws_im = nullptr; pl.ws_elems = 0;
+        CUDA_TRY(cudaMalloc(&pl.ws_re, chunk * pl.n * sizeof(T)));
+        CUDA_TRY(cudaMalloc(&pl.ws_im, chunk * pl.n * sizeof(T)));
+        pl.ws_elems = chunk * pl.n;
+    }
+    // Workspace reuse is ordered by the stream itself when consecutive calls use the same stream;
+    // a call on a different stream first waits for the previous user.  While `stream` is being
+    // captured into a CUDA graph the cross-stream bookkeeping is skipped (the graph's owner orders
+    // replays against other users of the plan).
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (!capturing && pl.ws_last_stream != stream && pl.ws_used) CUDA_TRY(cudaStreamWaitEvent(stream, pl.ws_free, 0));
+    const int P = pl.num_passes;
+    for (size_t done = 0; done < batch; done += chunk) {
+        const size_t nb = std::min(chunk, batch - done);
+        for (int p = 0; p < P; ++p) {
+            memset(&prm, 0, sizeof(prm));
+            prm.scale = T(1);
+            if (p == 0) {
+                prm.in_re = io.in_re + (io.in_il ? 2 : 1) * done * io.in_bstride;
+                prm.in_im = io.in_im ? io.in_im + done * io.in_bstride : nullptr;
+                prm.in_bstride = io.in_bstride;
+                prm.in_interleaved = io.in_il;
+            } else {
+                prm.in_re = pl.ws_re; prm.in_im = pl.ws_im; prm.in_bstride = (long long)pl.n;
+            }
+            if (p == P - 1) {
+                prm.out_re = io.out_re + (io.out_il ? 2 : 1) * done * io.out_bstride;
+                prm.out_im = io.out_im ? io.out_im + done * io.out_bstride : nullptr;
+                prm.out_bstride = io.out_bstride;
+                prm.out_interleaved = io.out_il;
+                prm.scale = scale;
+            } else {
+                prm.out_re = pl.ws_re; prm.out_im = pl.ws_im; prm.out_bstride = (long long)pl.n;
+            }
+            if (pass_events && done == 0 && p == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
+            int32_t st = launch_pass(pl, p, prm, nb, stream);
+            if (st) return st;
+            if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[p + 1], stream));
+        }
+    }
+    if (!capturing) {
+        CUDA_TRY(cudaEventRecord(pl.ws_free, stream));
+        pl.ws_last_stream = stream;
+        pl.ws_used = true;
+    }
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t check_c2c_args(const Plan<T>* pl, size_t len_re, size_t len_im, int direction) {
+    if (!pl) return fail(PHASTFT_ERR_INVALID_ARG, "plan == NULL");
+    if (len_re != len_im) return fail(PHASTFT_ERR_LEN_MISMATCH);                      // dit.rs:284
+    if (!is_pow2(len_re)) return fail(PHASTFT_ERR_NOT_POW2);                          // dit.rs:285
+    if (ilog2(len_re) != pl->log2n) return fail(PHASTFT_ERR_PLAN_MISMATCH);           // dit.rs:289
+    if (direction != PHASTFT_FORWARD && direction != PHASTFT_REVERSE) return fail(PHASTFT_ERR_INVALID_ARG, "direction must be 1 or -1");
+    return PHASTFT_OK;
+}
+
+// planar, in place, device pointers ------------------------------------------------------------------
+template <typename T>
+int32_t fft_dev(const Plan<T>* pl, T* d_re, T* d_im, int direction, size_t batch, size_t bstride, cudaStream_t stream,
+                cudaEvent_t* pass_events = nullptr) {
+    if (!pl || !d_re || !d_im) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    if (direction != PHASTFT_FORWARD && direction != PHASTFT_REVERSE) return fail(PHASTFT_ERR_INVALID_ARG, "direction must be 1 or -1");
+    if (batch > 1 && bstride < pl->n) return fail(PHASTFT_ERR_INVALID_ARG, "batch_stride < N");
+    DeviceGuard g(pl->device);
+    Io<T> io;
+    // inverse via the swap trick (algorithms/dit.rs:297-300): forward transform of (imags, reals), then 1/N
+    if (direction == PHASTFT_FORWARD) { io.in_re = d_re; io.in_im = d_im; io.out_re = d_re; io.out_im = d_im; }
+    else { io.in_re = d_im; io.in_im = d_re; io.out_re = d_im; io.out_im = d_re; }
+    io.in_bstride = io.out_bstride = (long long)bstride;
+    io.in_il = io.out_il = 0;
+    const T scale = direction == PHASTFT_REVERSE ? T(1) / (T)pl->n : T(1);   // dit.rs:326
+    if (pl->num_passes == 0) return PHASTFT_OK;
+    return run_c2c(*pl, io, batch, scale, stream, pass_events);
+}
+
+// One profiled call: per-pass device time from CUDA events on the launching stream (synchronises).
+template <typename T>
+int32_t fft_dev_profile(const Plan<T>* pl, T* d_re, T* d_im, int direction, size_t batch, size_t bstride,
+                        cudaStream_t stream, float* pass_ms, int* num_passes) {
+    if (!pl || !pass_ms || !num_passes) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(pl->device);
+    *num_passes = pl->num_passes;
+    cudaEvent_t ev[MAX_PASSES + 1];
+    for (int i = 0; i <= pl->num_passes; ++i) CUDA_TRY(cudaEventCreate(&ev[i]));
+    int32_t st = fft_dev(pl, d_re, d_im, direction, batch, bstride, stream, ev);
+    if (st == PHASTFT_OK && pl->num_passes > 0) {
+        cudaError_t e = cudaEventSynchronize(ev[pl->num_passes]);
+        if (e != cudaSuccess) st = fail(PHASTFT_ERR_CUDA, cudaGetErrorString(e));
+        for (int i = 0; i < pl->num_passes && st == PHASTFT_OK; ++i) cudaEventElapsedTime(&pass_ms[i], ev[i], ev[i + 1]);
+    }
+    for (int i = 0; i <= pl->num_passes; ++i) cudaEventDestroy(ev[i]);
+    return st;
+}
+
+template <typename T>
+int32_t fft_interleaved_dev(const Plan<T>* pl, T* d_sig, int direction, size_t batch, size_t bstride, cudaStream_t stream) {
+    if (!pl || !d_sig) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    if (direction != PHASTFT_FORWARD && direction != PHASTFT_REVERSE) return fail(PHASTFT_ERR_INVALID_ARG, "direction must be 1 or -1");
+    if (batch > 1 && bstride < pl->n) return fail(PHASTFT_ERR_INVALID_ARG, "batch_stride < N");
+    DeviceGuard g(pl->device);
+    if (pl->num_passes == 0) return PHASTFT_OK;
+    Io<T> io;
+    io.in_re = d_sig; io.in_im = nullptr; io.out_re = d_sig; io.out_im = nullptr;
+    io.in_bstride = io.out_bstride = (long long)bstride;
+    io.in_il = io.out_il = direction == PHASTFT_FORWARD ? 1 : 2;
+    const T scale = direction == PHASTFT_REVERSE ? T(1) / (T)pl->n : T(1);
+    return run_c2c(*pl, io, batch, scale, stream);
+}
+
+template <typename T>
+int32_t ensure_staging(const Plan<T>* pl, size_t elems) {
+    if (pl->stage_elems >= elems) return PHASTFT_OK;
+    if (pl->stage_re) cudaFree(pl->stage_re);
+    if (pl->stage_im) cudaFree(pl->stage_im);
+    pl->stage_re = pl->stage_im = nullptr; pl->stage_elems = 0;
+    CUDA_TRY(cudaMalloc(&pl->stage_re, elems * sizeof(T)));
+    CUDA_TRY(cudaMalloc(&pl->stage_im, elems * sizeof(T)));
+    pl->stage_elems = elems;
+    return PHASTFT_OK;
+}
+
+// host slices: H2D, run, D2H, synchronous (lib.rs:143-150 semantics) ----------------------------------
+template <typename T>
+int32_t fft_host(const Plan<T>* pl, T* re, size_t len_re, T* im, size_t len_im, int direction) {
+    int32_t st = check_c2c_args(pl, len_re, len_im, direction);
+    if (st) return st;
+    if (!re || !im) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
+    DeviceGuard g(pl->device);
+    {
+        std::lock_guard<std::mutex> lock(pl->mu);
+        st = ensure_staging(pl, pl->n);
+        if (st) return st;
+    }
+    const size_t bytes = pl->n * sizeof(T);
+    CUDA_TRY(cudaMemcpyAsync(pl->stage_re, re, bytes, cudaMemcpyHostToDevice, pl->stream));
+    CUDA_TRY(cudaMemcpyAsync(pl->stage_im, im, bytes, cudaMemcpyHostToDevice, pl->stream));
+    st = fft_dev(pl, pl->stage_re, pl->stage_im, direction, 1, pl->n, pl->stream);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(re, pl->stage_re, bytes, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaMemcpyAsync(im, pl->stage_im, bytes, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t fft_interleaved_host(const Plan<T>* pl, T* sig, size_t len_complex, int direction) {
+    int32_t st = check_c2c_args(pl, len_complex, len_complex, direction);
+    if (st) return st;
+    if (!sig) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
+    DeviceGuard g(pl->device);
+    {
+        std::lock_guard<std::mutex> lock(pl->mu);
+        st = ensure_staging(pl, 2 * pl->n);
+        if (st) return st;
+    }
+    const size_t bytes = 2 * pl->n * sizeof(T);
+    CUDA_TRY(cudaMemcpyAsync(pl->stage_re, sig, bytes, cudaMemcpyHostToDevice, pl->stream));
+    st = fft_interleaved_dev(pl, pl->stage_re, direction, 1, pl->n, pl->stream);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(sig, pl->stage_re, bytes, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t fft_oneshot(T* re, size_t len_re, T* im, size_t len_im, int direction, int device) {
+    // lib.rs:180-183: PlannerDit::new(reals.len()) then the with_planner path
+    if (!is_pow2(len_re)) return fail(PHASTFT_ERR_NOT_POW2);
+    Plan<T>* pl = nullptr;
+    int32_t st = build_plan<T>(len_re, device, &pl);
+    if (st) return st;
+    st = fft_host(pl, re, len_re, im, len_im, direction);
+    delete pl;
+    return st;
+}
+
+template <typename T>
+int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, size_t batch, size_t bstride, int direction) {
+    if (!plans || num_plans <= 0 || !re || !im) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    if (direction != PHASTFT_FORWARD && direction != PHASTFT_REVERSE) return fail(PHASTFT_ERR_INVALID_ARG, "direction must be 1 or -1");
+    const size_t n = plans[0]->n;
+    for (int g = 0; g < num_plans; ++g)
+        if (!plans[g] || plans[g]->n != n) return fail(PHASTFT_ERR_PLAN_MISMATCH);
+    if (bstride < n) return fail(PHASTFT_ERR_INVALID_ARG, "batch_stride < N");
+    // contiguous ranges of transforms per device; no collective on the data path
+    std::vector<size_t> lo(num_plans + 1);
+    for (int g = 0; g <= num_plans; ++g) lo[g] = batch * g / num_plans;
+    for (int g = 0; g < num_plans; ++g) {
+        const Plan<T>* pl = plans[g];
+        const size_t nb = lo[g + 1] - lo[g];
+        if (!nb) continue;
+        DeviceGuard guard(pl->device);
+        {
+            std::lock_guard<std::mutex> lock(pl->mu);
+            int32_t st = ensure_staging(pl, nb * n);
+            if (st) return st;
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(pl->stage_re, n * sizeof(T), re + lo[g] * bstride, bstride * sizeof(T), n * sizeof(T), nb, cudaMemcpyHostToDevice, pl->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(pl->stage_im, n * sizeof(T), im + lo[g] * bstride, bstride * sizeof(T), n * sizeof(T), nb, cudaMemcpyHostToDevice, pl->stream));
+        int32_t st = fft_dev(pl, pl->stage_re, pl->stage_im, direction, nb, n, pl->stream);
+        if (st) return st;
+        CUDA_TRY(cudaMemcpy2DAsync(re + lo[g] * bstride, bstride * sizeof(T), pl->stage_re, n * sizeof(T), n * sizeof(T), nb, cudaMemcpyDeviceToHost, pl->stream));
+        CUDA_TRY(cudaMemcpy2DAsync(im + lo[g] * bstride, bstride * sizeof(T), pl->stage_im, n * sizeof(T), n * sizeof(T), nb, cudaMemcpyDeviceToHost, pl->stream));
+    }
+    for (int g = 0; g < num_plans; ++g) {
+        DeviceGuard guard(plans[g]->device);
+        CUDA_TRY(cudaStreamSynchronize(plans[g]->stream));
+    }
+    return PHASTFT_OK;
+}
+
+// ---- table blob export / import / broadcast ------------------------------------------------------------
+template <typename T>
+int32_t tables_export(const Plan<T>* pl, void* dst, cudaStream_t s) {
+    if (!pl || !dst) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(pl->device);
+    CUDA_TRY(cudaMemcpyAsync(dst, pl->blob_dev, pl->blob_host.size(), cudaMemcpyDeviceToDevice, s));
+    return PHASTFT_OK;
+}
+template <typename T>
+int32_t tables_import(Plan<T>* pl, const void* src, cudaStream_t s) {
+    if (!pl || !src) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(pl->device);
+    CUDA_TRY(cudaMemcpyAsync(pl->blob_dev, src, pl->blob_host.size(), cudaMemcpyDeviceToDevice, s));
+    return PHASTFT_OK;
+}
+
+typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+template <typename T>
+int32_t tables_broadcast(Plan<T>* pl, void* comm, int root, cudaStream_t s) {
+    if (!pl || !comm) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    static nccl_bcast_fn bcast = [] {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        return h ? reinterpret_cast<nccl_bcast_fn>(dlsym(h, "ncclBroadcast")) : nullptr;
+    }();
+    if (!bcast) return fail(PHASTFT_ERR_NCCL, "libnccl.so.2 / ncclBroadcast not found");
+    DeviceGuard g(pl->device);
+    int rc = bcast(pl->blob_dev, pl->blob_dev, pl->blob_host.size(), /*ncclChar*/ 0, root, comm, s);
+    if (rc != 0) return fail(PHASTFT_ERR_NCCL, "ncclBroadcast returned " + std::to_string(rc));
+    return PHASTFT_OK;
+}
+
+// =================================================================================================
+// r2c / c2r
+// =================================================================================================
+template <typename T>
+struct PlanR2c {
+    size_t n = 0;
+    int device = 0;
+    Plan<T>* inner = nullptr;          // half-length c2c (planner.rs:203)
+    unsigned char* tw_dev = nullptr;   // two-level W_n table for the untangle / preprocess twiddles
+    size_t hi_elems = 0, lo_elems = 0;
+    int lo_bits = 0;
+    mutable std::mutex mu;
+    mutable T* d_real = nullptr;       // host-API staging: N reals
+    mutable T* d_spec_re = nullptr;    // N/2+1
+    mutable T* d_spec_im = nullptr;
+    mutable T* d_scr_re = nullptr;     // N/2 (c2r scratch when the caller passes none)
+    mutable T* d_scr_im = nullptr;
+    ~PlanR2c() {
+        DeviceGuard g(device);
+        for (void* p : {(void*)tw_dev, (void*)d_real, (void*)d_spec_re, (void*)d_spec_im, (void*)d_scr_re, (void*)d_scr_im})
+            if (p) cudaFree(p);
+        delete inner;
+    }
+};
+
+template <typename T>
+int32_t build_plan_r2c(size_t n, int device, PlanR2c<T>** out) {
+    if (!out) return fail(PHASTFT_ERR_INVALID_ARG, "out == NULL");
+    *out = nullptr;
+    if (!(n >= 4 && is_pow2(n))) return fail(PHASTFT_ERR_R2C_N);   // planner.rs:195
+    if (n > (size_t(1) << 31)) return fail(PHASTFT_ERR_INVALID_ARG, "n > 2^31 not supported");
+    std::unique_ptr<PlanR2c<T>> pl(new PlanR2c<T>());
+    pl->n = n; pl->device = device;
+    int32_t st = build_plan<T>(n / 2, device, &pl->inner);
+    if (st) return st;
+    DeviceGuard g(device);
+    const int ln = ilog2(n);
+    pl->lo_bits = (ln + 1) / 2;
+    pl->lo_elems = size_t(1) << pl->lo_bits;
+    pl->hi_elems = size_t(1) << (ln - pl->lo_bits);
+    std::vector<double2> tab(pl->hi_elems + pl->lo_elems);
+    for (size_t h = 0; h < pl->hi_elems; ++h) root_of_unity((uint64_t)h << pl->lo_bits, n, tab[h].x, tab[h].y);
+    for (size_t l = 0; l < pl->lo_elems; ++l) root_of_unity(l, n, tab[pl->hi_elems + l].x, tab[pl->hi_elems + l].y);
+    CUDA_TRY(cudaMalloc(&pl->tw_dev, tab.size() * sizeof(double2)));
+    CUDA_TRY(cudaMemcpy(pl->tw_dev, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    // c2r scratch for the allocating variants lives in the plan (r2c.rs:716-718 allocates per call)
+    CUDA_TRY(cudaMalloc(&pl->d_scr_re, (n / 2) * sizeof(T)));
+    CUDA_TRY(cudaMalloc(&pl->d_scr_im, (n / 2) * sizeof(T)));
+    *out = pl.release();
+    return PHASTFT_OK;
+}
+
+template <typename T>
+Tw2 r2c_tw2(const PlanR2c<T>* pl) {
+    Tw2 t;
+    t.hi = reinterpret_cast<const double2*>(pl->tw_dev);
+    t.lo = t.hi + pl->hi_elems;
+    t.lo_bits = pl->lo_bits;
+    return t;
+}
+
+template <typename T>
+int32_t r2c_dev(const PlanR2c<T>* pl, const T* d_in, T* d_ore, T* d_oim, cudaStream_t stream) {
+    if (!pl || !d_in || !d_ore || !d_oim) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    DeviceGuard g(pl->device);
+    const size_t half = pl->n / 2;
+    // (1)+(2) deinterleave fused into the first pass load: z[k] = x[2k] + i x[2k+1] (r2c.rs:557-569),
+    //         half-length forward c2c into output[..half] (r2c.rs:575)
+    Io<T> io;
+    io.in_re = d_in; io.in_im = nullptr; io.in_il = 1; io.in_bstride = (long long)half;
+    io.out_re = d_ore; io.out_im = d_oim; io.out_il = 0; io.out_bstride = (long long)half;
+    int32_t st;
+    if (pl->inner->num_passes == 0) return fail(PHASTFT_ERR_INVALID_ARG, "unreachable: half >= 2");
+    st = run_c2c(*pl->inner, io, 1, T(1), stream);
+    if (st) return st;
+    // (3) untangle in place over all half+1 slots (r2c.rs:584-592)
+    RealParams<T> rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.re = d_ore; rp.im = d_oim; rp.log2half = ilog2(half); rp.tw2 = r2c_tw2(pl);
+    const size_t q = half / 2;
+    dim3 grid((unsigned)((q + 1 + 255) / 256), 1);
+    r2c_untangle_kernel<T><<<grid, 256, 0, stream>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t c2r_dev(const PlanR2c<T>* pl, const T* d_ire, const T* d_iim, T* d_out, T* d_sre, T* d_sim, cudaStream_t stream) {
+    if (!pl || !d_ire || !d_iim || !d_out) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    if ((d_sre == nullptr) != (d_sim == nullptr)) return fail(PHASTFT_ERR_INVALID_ARG, "pass both scratch arrays or neither");
+    DeviceGuard g(pl->device);
+    const size_t half = pl->n / 2;
+    std::unique_lock<std::mutex> lock(pl->mu, std::defer_lock);
+    if (!d_sre) { lock.lock(); d_sre = pl->d_scr_re; d_sim = pl->d_scr_im; }
+    // (1) pre-process into scratch (r2c.rs:764-780)
+    RealParams<T> rp;
+    memset(&rp, 0, sizeof(rp));
+    rp.re = d_sre; rp.im = d_sim; rp.in_re = d_ire; rp.in_im = d_iim; rp.log2half = ilog2(half); rp.tw2 = r2c_tw2(pl);
+    dim3 grid((unsigned)((half + 255) / 256), 1);
+    c2r_preprocess_kernel<T><<<grid, 256, 0, stream>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    // (2) inverse half-length c2c on the scratch (swap trick + 1/half, r2c.rs:782) with
+    // (3) the re-interleave into the real output (r2c.rs:790-798) fused into the last store
+    Io<T> io;
+    io.in_re = d_sim; io.in_im = d_sre; io.in_il = 0; io.in_bstride = (long long)half;
+    io.out_re = d_out; io.out_im = nullptr; io.out_il = 2; io.out_bstride = (long long)half;
+    return run_c2c(*pl->inner, io, 1, T(1) / (T)half, stream);
+}
+
+template <typename T>
+int32_t ensure_r2c_staging(const PlanR2c<T>* pl) {
+    const size_t half = pl->n / 2;
+    if (!pl->d_real) CUDA_TRY(cudaMalloc(&pl->d_real, pl->n * sizeof(T)));
+    if (!pl->d_spec_re) CUDA_TRY(cudaMalloc(&pl->d_spec_re, (half + 1) * sizeof(T)));
+    if (!pl->d_spec_im) CUDA_TRY(cudaMalloc(&pl->d_spec_im, (half + 1) * sizeof(T)));
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t r2c_host(const PlanR2c<T>* pl, const T* in, size_t len_in, T* ore, size_t len_ore, T* oim, size_t len_oim) {
+    if (!pl) return fail(PHASTFT_ERR_INVALID_ARG, "plan == NULL");
+    const size_t n = pl->n, half = n / 2;
+    if (len_in != n) return fail(PHASTFT_ERR_INPUT_LEN);              // r2c.rs:543
+    if (len_ore != half + 1) return fail(PHASTFT_ERR_OUTPUT_RE_LEN);  // r2c.rs:544
+    if (len_oim != half + 1) return fail(PHASTFT_ERR_OUTPUT_IM_LEN);  // r2c.rs:549
+    if (!in || !ore || !oim) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
+    DeviceGuard g(pl->device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    int32_t st = ensure_r2c_staging(pl);
+    if (st) return st;
+    cudaStream_t s = pl->inner->stream;
+    CUDA_TRY(cudaMemcpyAsync(pl->d_real, in, n * sizeof(T), cudaMemcpyHostToDevice, s));
+    st = r2c_dev(pl, pl->d_real, pl->d_spec_re, pl->d_spec_im, s);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(ore, pl->d_spec_re, (half + 1) * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(oim, pl->d_spec_im, (half + 1) * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t c2r_host(const PlanR2c<T>* pl, const T* ire, size_t len_ire, const T* iim, size_t len_iim, T* out, size_t len_out,
+                 T* sre, size_t len_sre, T* sim, size_t len_sim) {
+    if (!pl) return fail(PHASTFT_ERR_INVALID_ARG, "plan == NULL");
+    const size_t n = pl->n, half = n / 2;
+    if (len_out != n) return fail(PHASTFT_ERR_OUTPUT_LEN);            // r2c.rs:750
+    if (len_ire != half + 1) return fail(PHASTFT_ERR_INPUT_RE_LEN);   // r2c.rs:751
+    if (len_iim != half + 1) return fail(PHASTFT_ERR_INPUT_IM_LEN);   // r2c.rs:756
+    const bool has_scratch = sre || sim || len_sre || len_sim;
+    if (has_scratch) {
+        if (len_sre != half) return fail(PHASTFT_ERR_SCRATCH_RE_LEN);  // r2c.rs:761
+        if (len_sim != half) return fail(PHASTFT_ERR_SCRATCH_IM_LEN);  // r2c.rs:762
+    }
+    if (!ire || !iim || !out) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
+    DeviceGuard g(pl->device);
+    cudaStream_t s = pl->inner->stream;
+    {
+        std::lock_guard<std::mutex> lock(pl->mu);
+        int32_t st = ensure_r2c_staging(pl);
+        if (st) return st;
+    }
+    CUDA_TRY(cudaMemcpyAsync(pl->d_spec_re, ire, (half + 1) * sizeof(T), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(pl->d_spec_im, iim, (half + 1) * sizeof(T), cudaMemcpyHostToDevice, s));
+    int32_t st = c2r_dev<T>(pl, pl->d_spec_re, pl->d_spec_im, pl->d_real, nullptr, nullptr, s);
+    if (st) return st;
+    CUDA_TRY(cudaMemcpyAsync(out, pl->d_real, n * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return PHASTFT_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define AS_PLAN(T, p) reinterpret_cast<Plan<T>*>(p)
+#define AS_CPLAN(T, p) reinterpret_cast<const Plan<T>*>(p)
+#define AS_R2C(T, p) reinterpret_cast<PlanR2c<T>*>(p)
+#define AS_CR2C(T, p) reinterpret_cast<const PlanR2c<T>*>(p)
+
+extern "C" {
+
+const char* phastft_last_error(void) { return g_last_error.c_str(); }
+const char* phastft_version(void) { return "phastft_cuda 0.1.0 (sm_100a)"; }
+uint64_t phastft_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int32_t phastft_device_count(int* count) {
+    if (!count) return fail(PHASTFT_ERR_INVALID_ARG, "count == NULL");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess || *count == 0) { *count = 0; return fail(PHASTFT_ERR_NO_DEVICE, e != cudaSuccess ? cudaGetErrorString(e) : ""); }
+    return PHASTFT_OK;
+}
+
+void phastft_options_default(phastft_options* out) {
+    if (!out) return;
+    out->multithreaded_bit_reversal = 0;
+    out->smallest_parallel_chunk_size = 16384;
+}
+void phastft_options_guess(size_t input_size, phastft_options* out) {
+    if (!out) return;
+    phastft_options_default(out);
+    out->multithreaded_bit_reversal = input_size ? (ilog2(input_size) >= 16) : 0;
+}
+
+#define DEFINE_DIT_API(T, SFX)                                                                                          \
+    int32_t phastft_plan_dit_##SFX##_create(size_t n, int device, int mode, phastft_plan_dit_##SFX** out) {             \
+        (void)mode; /* planner.rs:65: the reference ignores the mode as well */                                         \
+        Plan<T>* pl = nullptr;                                                                                          \
+        int32_t st = build_plan<T>(n, device, &pl);                                                                     \
+        if (out) *out = reinterpret_cast<phastft_plan_dit_##SFX*>(pl);                                                  \
+        else if (pl) delete pl;                                                                                         \
+        return st;                                                                                                      \
+    }                                                                                                                   \
+    void phastft_plan_dit_##SFX##_destroy(phastft_plan_dit_##SFX* p) { delete AS_PLAN(T, p); }                          \
+    size_t phastft_plan_dit_##SFX##_size(const phastft_plan_dit_##SFX* p) { return p ? AS_CPLAN(T, p)->n : 0; }         \
+    const char* phastft_plan_dit_##SFX##_describe(const phastft_plan_dit_##SFX* p) {                                    \
+        return p ? AS_CPLAN(T, p)->description.c_str() : "";                                                            \
+    }                                                                                                                   \
+    size_t phastft_plan_dit_##SFX##_tables_bytes(const phastft_plan_dit_##SFX* p) {                                     \
+        return p ? AS_CPLAN(T, p)->blob_host.size() : 0;                                                                \
+    }                                                                                                                   \
+    int32_t phastft_plan_dit_##SFX##_tables_export(const phastft_plan_dit_##SFX* p, void* dst, void* s) {               \
+        return tables_export<T>(AS_CPLAN(T, p), dst, (cudaStream_t)s);                                                  \
+    }                                                                                                                   \
+    int32_t phastft_plan_dit_##SFX##_tables_import(phastft_plan_dit_##SFX* p, const void* src, void* s) {               \
+        return tables_import<T>(AS_PLAN(T, p), src, (cudaStream_t)s);                                                   \
+    }                                                                                                                   \
+    int32_t phastft_plan_dit_##SFX##_tables_broadcast(phastft_plan_dit_##SFX* p, void* comm, int root, void* s) {       \
+        return tables_broadcast<T>(AS_PLAN(T, p), comm, root, (cudaStream_t)s);                                         \
+    }                                                                                                                   \
+    int32_t phastft_fft_dit_##SFX##_host(const phastft_plan_dit_##SFX* p, T* re, size_t lre, T* im, size_t lim,        \
+                                         int dir, const phastft_options* opts) {                                        \
+        (void)opts;                                                                                                     \
+        return fft_host<T>(AS_CPLAN(T, p), re, lre, im, lim, dir);                                                      \
+    }                                                                                                                   \
+    int32_t phastft_fft_dit_##SFX##_oneshot(T* re, size_t lre, T* im, size_t lim, int dir, int device) {                \
+        return fft_oneshot<T>(re, lre, im, lim, dir, device);                                                           \
+    }                                                                                                                   \
+    int32_t phastft_fft_dit_##SFX##_dev(const phastft_plan_dit_##SFX* p, T* re, T* im, int dir, size_t batch,          \
+                                        size_t bstride, void* s) {                                                      \
+        return fft_dev<T>(AS_CPLAN(T, p), re, im, dir, batch, bstride, (cudaStream_t)s);                                \
+    }                                                                                                                   \
+    int32_t phastft_fft_dit_##SFX##_dev_profile(const phastft_plan_dit_##SFX* p, T* re, T* im, int dir, size_t batch,  \
+                                                size_t bstride, void* s, float* pass_ms, int* num_passes) {             \
+        return fft_dev_profile<T>(AS_CPLAN(T, p), re, im, dir, batch, bstride, (cudaStream_t)s, pass_ms, num_passes);   \
+    }                                                                                                                   \
+    int32_t phastft_fft_dit_##SFX##_batch_sharded_host(phastft_plan_dit_##SFX* const* plans, int np, T* re, T* im,     \
+                                                       size_t batch, size_t bstride, int dir) {                         \
+        return batch_sharded_host<T>(reinterpret_cast<Plan<T>* const*>(plans), np, re, im, batch, bstride, dir);        \
+    }                                                                                                                   \
+    int32_t phastft_fft_interleaved_##SFX##_host(const phastft_plan_dit_##SFX* p, T* sig, size_t len, int dir) {        \
+        return fft_interleaved_host<T>(AS_CPLAN(T, p), sig, len, dir);                                                  \
+    }                                                                                                                   \
+    int32_t phastft_fft_interleaved_##SFX##_dev(const phastft_plan_dit_##SFX* p, T* sig, int dir, size_t batch,        \
+                                                size_t bstride, void* s) {                                              \
+        return fft_interleaved_dev<T>(AS_CPLAN(T, p), sig, dir, batch, bstride, (cudaStream_t)s);                       \
+    }                                                                                                                   \
+    int32_t phastft_plan_r2c_##SFX##_create(size_t n, int device, phastft_plan_r2c_##SFX** out) {                       \
+        PlanR2c<T>* pl = nullptr;                                                                                       \
+        int32_t st = build_plan_r2c<T>(n, device, &pl);                                                                 \
+        if (out) *out = reinterpret_cast<phastft_plan_r2c_##SFX*>(pl);                                                  \
+        else if (pl) delete pl;                                                                                         \
+        return st;                                                                                                      \
+    }                                                                                                                   \
+    void phastft_plan_r2c_##SFX##_destroy(phastft_plan_r2c_##SFX* p) { delete AS_R2C(T, p); }                           \
+    size_t phastft_plan_r2c_##SFX##_size(const phastft_plan_r2c_##SFX* p) { return p ? AS_CR2C(T, p)->n : 0; }          \
+    int32_t phastft_r2c_##SFX##_host(const phastft_plan_r2c_##SFX* p, const T* in, size_t lin, T* ore, size_t lore,    \
+                                     T* oim, size_t loim) {                                                             \
+        return r2c_host<T>(AS_CR2C(T, p), in, lin, ore, lore, oim, loim);                                               \
+    }                                                                                                                   \
+    int32_t phastft_r2c_##SFX##_oneshot(const T* in, size_t lin, T* ore, size_t lore, T* oim, size_t loim, int dev) {   \
+        PlanR2c<T>* pl = nullptr;                                                                                       \
+        int32_t st = build_plan_r2c<T>(lin, dev, &pl); /* r2c.rs:522: PlannerR2c::new(input_re.len()) */                \
+        if (st) return st;                                                                                              \
+        st = r2c_host<T>(pl, in, lin, ore, lore, oim, loim);                                                            \
+        delete pl;                                                                                                      \
+        return st;                                                                                                      \
+    }                                                                                                                   \
+    int32_t phastft_r2c_##SFX##_dev(const phastft_plan_r2c_##SFX* p, const T* in, T* ore, T* oim, void* s) {            \
+        return r2c_dev<T>(AS_CR2C(T, p), in, ore, oim, (cudaStream_t)s);                                                \
+    }                                                                                                                   \
+    int32_t phastft_c2r_##SFX##_host(const phastft_plan_r2c_##SFX* p, const T* ire, size_t lire, const T* iim,          \
+                                     size_t liim, T* out, size_t lout, T* sre, size_t lsre, T* sim, size_t lsim) {      \
+        return c2r_host<T>(AS_CR2C(T, p), ire, lire, iim, liim, out, lout, sre, lsre, sim, lsim);                       \
+    }                                                                                                                   \
+    int32_t phastft_c2r_##SFX##_oneshot(const T* ire, size_t lire, const T* iim, size_t liim, T* out, size_t lout,     \
+                                        int dev) {                                                                      \
+        PlanR2c<T>* pl = nullptr;                                                                                       \
+        int32_t st = build_plan_r2c<T>(lout, dev, &pl); /* r2c.rs:696: PlannerR2c::new(output.len()) */                 \
+        if (st) return st;                                                                                              \
+        st = c2r_host<T>(pl, ire, lire, iim, liim, out, lout, nullptr, 0, nullptr, 0);                                  \
+        delete pl;                                                                                                      \
+        return st;                                                                                                      \
+    }                                                                                                                   \
+    int32_t phastft_c2r_##SFX##_dev(const phastft_plan_r2c_##SFX* p, const T* ire, const T* iim, T* out, T* sre,        \
+                                    T* sim, void* s) {                                                                  \
+        return c2r_dev<T>(AS_CR2C(T, p), ire, iim, out, sre, sim, (cudaStream_t)s);                                     \
+    }
+
+DEFINE_DIT_API(double, f64)
+DEFINE_DIT_API(float, f32)
+
+}  // extern "C"

@@ -1,0 +1,95 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/phastft_cuda.h declares; argument validation that precedes any CUDA call maps to the
+reference's panic messages; without a GPU the library refuses to run (no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def pf():
+    import __graft_entry__ as g
+    g.build()
+    import phastft_b200
+    return phastft_b200
+
+
+def declared_symbols():
+    text = (ROOT / "include" / "phastft_cuda.h").read_text()
+    return sorted(set(re.findall(r"PHASTFT_API\s+[\w\s\*]+?\b(phastft_\w+)\s*\(", text)))
+
+
+def test_header_declares_expected_surface():
+    syms = declared_symbols()
+    assert len(syms) >= 50
+    for must in ("phastft_fft_dit_f64_host", "phastft_fft_dit_f32_dev", "phastft_r2c_f64_dev", "phastft_c2r_f32_host",
+                 "phastft_plan_dit_f64_tables_broadcast", "phastft_fft_dit_f32_batch_sharded_host"):
+        assert must in syms
+
+
+def test_library_exports_every_declared_symbol(pf):
+    lib = ctypes.CDLL(str(pf.LIB_PATH))
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_every_declared_symbol(pf):
+    from phastft_b200 import _lib
+    bound = {name.format(s=s) for name in _lib.SIGNATURES for s in ("f64", "f32")} | set(_lib.GLOBAL_SYMBOLS)
+    assert set(declared_symbols()) <= bound
+
+
+def test_status_messages_match_reference_panics():
+    # include/phastft_status.h and the Python table must agree on the reference's panic texts
+    text = (ROOT / "include" / "phastft_status.h").read_text()
+    from phastft_b200 import _lib
+    for code, msg in _lib.MESSAGES.items():
+        if 4 <= code <= 12:
+            assert f'return "{msg}";' in text, msg
+
+
+def test_validation_before_cuda(pf):
+    # planner.rs:66 and planner.rs:195 are checked before any device is touched
+    for P in (pf.PlannerDit64, pf.PlannerDit32):
+        for bad in (0, 3, 5, 1000):
+            with pytest.raises(pf.PhastFTPanic) as e:
+                P(bad)
+            assert e.value.code == 2
+    for P in (pf.PlannerR2c64, pf.PlannerR2c32):
+        for bad in (0, 1, 2, 3, 6, 100):
+            with pytest.raises(pf.PhastFTPanic, match="n must be a power of 2 >= 4"):
+                P(bad)
+
+
+def test_no_cpu_fallback(pf):
+    if pf.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pf.PhastFTPanic) as e:
+        pf.PlannerDit64(1024)
+    assert e.value.code == 102
+    re_ = np.zeros(16); im_ = np.zeros(16)
+    with pytest.raises(pf.PhastFTPanic) as e:
+        pf.fft_64_dit(re_, im_, pf.Direction.Forward)
+    assert e.value.code == 102
+    assert pf.launch_count() == 0
+
+
+def test_options_mirror(pf):
+    # options.rs:26-43
+    o = pf.Options()
+    assert o.multithreaded_bit_reversal is False and o.smallest_parallel_chunk_size == 16384
+    assert pf.Options.guess_options(1 << 15).multithreaded_bit_reversal is False
+    assert pf.Options.guess_options(1 << 16).multithreaded_bit_reversal is True
+    assert int(pf.Direction.Forward) == 1 and int(pf.Direction.Reverse) == -1
+
+
+def test_product_never_imports_the_oracle():
+    for p in (ROOT / "phastft_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".hpp"):
+            assert "oracle" not in p.read_text().lower().replace("the cpu oracle", "").replace("oracle/", "ORACLEDIR") \
+                or p.name == "__init__.py", p

@@ -1,0 +1,310 @@
+"""GPU parity tests for the c2c path, all through the C ABI (phastft_b200.api -> libphastft_cuda.so).
+
+Checker = the CPU oracle (oracle/) on the same seeded inputs, the committed golden vectors, and
+size-independent properties at BASELINE.json's full sizes.  Tolerance (stated once, used
+everywhere): relative L-infinity  max|X_gpu - X_ref| / max|X_ref|  <=  C_TOL * eps * log2(N),
+eps = 2^-52 (f64) / 2^-23 (f32), C_TOL = 4.
+"""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = Path(__file__).resolve().parent / "golden"
+C_TOL = 4.0
+
+
+def _pf():
+    import phastft_b200 as pf
+    return pf
+
+
+def _O():
+    from oracle import oracle as O
+    return O
+
+
+def tol(dt, n):
+    return C_TOL * np.finfo(dt).eps * max(np.log2(n), 1.0)
+
+
+def rel_linf(a_re, a_im, b_re, b_im):
+    a = np.asarray(a_re, np.float64) + 1j * np.asarray(a_im, np.float64)
+    b = np.asarray(b_re, np.float64) + 1j * np.asarray(b_im, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), np.finfo(np.float64).tiny))
+
+
+def planner_for(dt, n):
+    pf = _pf()
+    return (pf.PlannerDit64 if dt == np.float64 else pf.PlannerDit32)(n, 0)
+
+
+def fft_with_planner(dt):
+    pf = _pf()
+    return pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
+
+
+def fft_oneshot(dt):
+    pf = _pf()
+    return pf.fft_64_dit if dt == np.float64 else pf.fft_32_dit
+
+
+# ------------------------------------------------------------------------------------------------
+# every power of two from 1 to 2^22 against the oracle, forward and reverse, host-slice API
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("log_n", list(range(0, 23)))
+def test_forward_and_reverse_vs_oracle(dt, log_n):
+    pf, O = _pf(), _O()
+    n = 1 << log_n
+    re0, im0 = O.gen_random_signal(n, dt, seed=1234 + log_n)
+    planner = planner_for(dt, n)
+    for direction, odir in ((pf.Direction.Forward, O.FORWARD), (pf.Direction.Reverse, O.REVERSE)):
+        g_re, g_im = re0.copy(), im0.copy()
+        fft_with_planner(dt)(g_re, g_im, direction, planner)
+        o_re, o_im = re0.copy(), im0.copy()
+        O.fft_dit(o_re, o_im, odir)
+        err = rel_linf(g_re, g_im, o_re, o_im)
+        assert err <= tol(dt, n), (planner.describe(), direction, err)
+    # independent truth as well (numpy pocketfft, f64)
+    truth = np.fft.fft(re0.astype(np.float64) + 1j * im0.astype(np.float64))
+    g_re, g_im = re0.copy(), im0.copy()
+    fft_with_planner(dt)(g_re, g_im, pf.Direction.Forward, planner)
+    assert rel_linf(g_re, g_im, truth.real, truth.imag) <= tol(dt, n)
+
+
+# --- committed golden vectors; the GPU must be at least as close to the truth as ~2x the oracle --
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_golden_vectors(dt):
+    pf, O = _pf(), _O()
+    g = np.load(GOLD / "c2c_golden.npz")
+    for n in (1, 2, 4, 8, 16, 32, 64, 128, 256, 1024, 4096):
+        re = g[f"rand_{n}_in_re"].astype(dt); im = g[f"rand_{n}_in_im"].astype(dt)
+        o_re, o_im = re.copy(), im.copy()
+        O.fft_dit(o_re, o_im, O.FORWARD)
+        fft_oneshot(dt)(re, im, pf.Direction.Forward)
+        e_gpu = rel_linf(re, im, g[f"rand_{n}_out_re"], g[f"rand_{n}_out_im"])
+        e_orc = rel_linf(o_re, o_im, g[f"rand_{n}_out_re"], g[f"rand_{n}_out_im"])
+        assert e_gpu <= tol(dt, n), (n, e_gpu)
+        assert e_gpu <= 2 * e_orc + 2 * np.finfo(dt).eps, (n, e_gpu, e_orc)
+    for n in (16, 64, 256, 1024):
+        re = np.arange(1, n + 1, dtype=dt); im = re.copy()
+        fft_oneshot(dt)(re, im, pf.Direction.Forward)
+        assert rel_linf(re, im, g[f"ramp_{n}_out_re"], g[f"ramp_{n}_out_im"]) <= tol(dt, n)
+
+
+# --- the reference's own tests, restated through the mirror API -----------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 2, 4, 16, 1024, 1 << 14, 1 << 17])
+def test_impulse_gives_all_ones(dt, n):            # lib.rs:171-178 doctest
+    pf = _pf()
+    re = np.zeros(n, dt); im = np.zeros(n, dt); re[0] = 1
+    fft_oneshot(dt)(re, im, pf.Direction.Forward)
+    assert np.max(np.abs(re - 1)) <= 8 * np.finfo(dt).eps and np.max(np.abs(im)) <= 8 * np.finfo(dt).eps
+
+
+@pytest.mark.parametrize("dt,ks", [(np.float32, range(4, 9)), (np.float64, range(4, 17))])
+def test_fft_correctness_ramp(dt, ks):             # lib.rs:298-338, abs 0.01
+    pf = _pf()
+    for k in ks:
+        n = 1 << k
+        re = np.arange(1, n + 1, dtype=dt); im = re.copy()
+        fft_oneshot(dt)(re, im, pf.Direction.Forward)
+        ref = np.fft.fft(np.arange(1, n + 1, dtype=np.float64) * (1 + 1j))
+        assert np.max(np.abs(re - ref.real)) < 0.01 and np.max(np.abs(im - ref.imag)) < 0.01
+
+
+@pytest.mark.parametrize("dt,eps", [(np.float64, 1e-10), (np.float32, 1e-7)])
+def test_fft_followed_by_ifft(dt, eps):            # lib.rs:380-425
+    pf, O = _pf(), _O()
+    for k in range(4, 12):
+        n = 1 << k
+        re0, im0 = O.gen_random_signal(n, dt, seed=k)
+        re, im = re0.copy(), im0.copy()
+        fft_oneshot(dt)(re, im, pf.Direction.Forward)
+        fft_oneshot(dt)(re, im, pf.Direction.Reverse)
+        assert np.max(np.abs(re - re0)) < eps and np.max(np.abs(im - im0)) < eps
+
+
+def test_tune_mode_roundtrip():                     # lib.rs:427-461
+    pf, O = _pf(), _O()
+    for k in range(5, 12):
+        n = 1 << k
+        re0, im0 = O.gen_random_signal(n, np.float64, seed=k)
+        planner = pf.PlannerDit64.with_mode(n, pf.PlannerMode.Tune)
+        re, im = re0.copy(), im0.copy()
+        pf.fft_64_dit_with_planner(re, im, pf.Direction.Forward, planner)
+        pf.fft_64_dit_with_planner(re, im, pf.Direction.Reverse, planner)
+        assert np.max(np.abs(re - re0)) < 1e-10 and np.max(np.abs(im - im0)) < 1e-10
+        pf.PlannerDit32.with_mode(n, pf.PlannerMode.Tune)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_panics(dt):                                # lib.rs:238-296, dit.rs:284-289
+    pf = _pf()
+    P = pf.PlannerDit64 if dt == np.float64 else pf.PlannerDit32
+    with pytest.raises(pf.PhastFTPanic) as e:
+        P(5)
+    assert e.value.code == 2
+    with pytest.raises(pf.PhastFTPanic):
+        P(0)
+    planner = P(16)
+    with pytest.raises(pf.PhastFTPanic) as e:       # wrong_num_points_in_planner
+        fft_with_planner(dt)(np.zeros(1 << 16, dt), np.zeros(1 << 16, dt), pf.Direction.Forward, planner)
+    assert e.value.code == 3
+    with pytest.raises(pf.PhastFTPanic) as e:
+        fft_with_planner(dt)(np.zeros(16, dt), np.zeros(8, dt), pf.Direction.Forward, planner)
+    assert e.value.code == 1
+    with pytest.raises(pf.PhastFTPanic) as e:
+        fft_with_planner(dt)(np.zeros(12, dt), np.zeros(12, dt), pf.Direction.Forward, planner)
+    assert e.value.code == 2
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_planner_matches_convenience_bit_exact(dt):
+    pf, O = _pf(), _O()
+    for n in (256, 1 << 15):
+        re0, im0 = O.gen_random_signal(n, dt)
+        a, b = re0.copy(), im0.copy(); fft_oneshot(dt)(a, b, pf.Direction.Forward)
+        c, d = re0.copy(), im0.copy(); fft_with_planner(dt)(c, d, pf.Direction.Forward, planner_for(dt, n))
+        e, f = re0.copy(), im0.copy()
+        opts = pf.Options.guess_options(n)
+        (pf.fft_64_dit_with_planner_and_opts if dt == np.float64 else pf.fft_32_dit_with_planner_and_opts)(
+            e, f, pf.Direction.Forward, planner_for(dt, n), opts)
+        assert np.array_equal(a, c) and np.array_equal(b, d) and np.array_equal(a, e) and np.array_equal(b, f)
+
+
+# --- interleaved Complex<T> API (lib.rs:340-378) -------------------------------------------------------
+@pytest.mark.parametrize("dt,cdt", [(np.float64, np.complex128), (np.float32, np.complex64)])
+@pytest.mark.parametrize("n", [2, 64, 1024, 1 << 15, 1 << 21])
+def test_interleaved_matches_planar(dt, cdt, n):
+    pf, O = _pf(), _O()
+    re0, im0 = O.gen_random_signal(n, dt, seed=n)
+    sig = (re0 + 1j * im0).astype(cdt)
+    re, im = re0.copy(), im0.copy()
+    fft_oneshot(dt)(re, im, pf.Direction.Forward)
+    (pf.fft_64_interleaved if dt == np.float64 else pf.fft_32_interleaved)(sig, pf.Direction.Forward)
+    assert np.array_equal(sig.real, re) and np.array_equal(sig.imag, im)
+    (pf.fft_64_interleaved if dt == np.float64 else pf.fft_32_interleaved)(sig, pf.Direction.Reverse)
+    fft_oneshot(dt)(re, im, pf.Direction.Reverse)
+    assert np.array_equal(sig.real, re) and np.array_equal(sig.imag, im)
+    assert np.max(np.abs(sig.real - re0)) < (1e-10 if dt == np.float64 else 1e-6)
+
+
+# --- device-resident (torch) path and batches -----------------------------------------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,batch", [(8, 1000), (256, 37), (4096, 9), (1 << 13, 5), (1 << 16, 6), (1 << 21, 2)])
+def test_device_batch_matches_host_single(dt, n, batch):
+    import torch
+    pf, O = _pf(), _O()
+    rng = np.random.default_rng(n + batch)
+    stride = n + (0 if batch % 2 else 16)           # exercise batch_stride > N as well
+    re_h = rng.uniform(-1, 1, batch * stride).astype(dt)
+    im_h = rng.uniform(-1, 1, batch * stride).astype(dt)
+    planner = planner_for(dt, n)
+    d_re = torch.from_numpy(re_h).cuda(); d_im = torch.from_numpy(im_h).cuda()
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, planner, batch, stride)
+    g_re = d_re.cpu().numpy(); g_im = d_im.cpu().numpy()
+    for b in range(batch):
+        s = slice(b * stride, b * stride + n)
+        a, c = re_h[s].copy(), im_h[s].copy()
+        fft_with_planner(dt)(a, c, pf.Direction.Forward, planner)
+        assert np.array_equal(g_re[s], a) and np.array_equal(g_im[s], c), (n, b)   # deterministic kernels: bit exact
+        if stride > n:                               # padding between transforms untouched
+            pad = slice(b * stride + n, (b + 1) * stride)
+            assert np.array_equal(g_re[pad], re_h[pad])
+    # oracle parity for the first and last members
+    for b in (0, batch - 1):
+        s = slice(b * stride, b * stride + n)
+        o_re, o_im = re_h[s].copy(), im_h[s].copy()
+        O.fft_dit(o_re, o_im, O.FORWARD)
+        assert rel_linf(g_re[s], g_im[s], o_re, o_im) <= tol(dt, n)
+
+
+def test_torch_tensor_single_and_stream():
+    import torch
+    pf, O = _pf(), _O()
+    n = 1 << 18
+    re0, im0 = O.gen_random_signal(n, np.float64)
+    planner = pf.PlannerDit64(n)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        d_re = torch.from_numpy(re0).cuda(); d_im = torch.from_numpy(im0).cuda()
+        pf.fft_64_dit_with_planner(d_re, d_im, pf.Direction.Forward, planner)
+        pf.fft_64_dit_with_planner(d_re, d_im, pf.Direction.Reverse, planner)
+    s.synchronize()
+    assert np.max(np.abs(d_re.cpu().numpy() - re0)) < 1e-12
+    with pytest.raises(pf.PhastFTPanic):
+        pf.fft_64_dit_with_planner(d_re[: n // 2].contiguous(), d_im[: n // 2].contiguous(), pf.Direction.Forward, planner)
+
+
+# --- BASELINE.json full sizes: oracle parity where the oracle finishes in seconds, else properties ----
+def test_config_2pow20_f64_forward_vs_oracle():
+    pf, O = _pf(), _O()
+    n = 1 << 20
+    re0, im0 = O.gen_random_signal(n, np.float64, seed=1234)
+    g_re, g_im = re0.copy(), im0.copy()
+    pf.fft_64_dit_with_planner(g_re, g_im, pf.Direction.Forward, pf.PlannerDit64(n))
+    o_re, o_im = re0.copy(), im0.copy()
+    O.fft_dit(o_re, o_im, O.FORWARD, parallel=True)
+    assert rel_linf(g_re, g_im, o_re, o_im) <= tol(np.float64, n)
+
+
+def test_config_2pow26_f64_properties_and_oracle():
+    import torch
+    pf, O = _pf(), _O()
+    n = 1 << 26
+    planner = pf.PlannerDit64(n)
+    rng = np.random.default_rng(1234)
+    re0 = rng.uniform(-1, 1, n); im0 = rng.uniform(-1, 1, n)
+    d_re = torch.from_numpy(re0).cuda(); d_im = torch.from_numpy(im0).cuda()
+    pf.fft_64_dit_with_planner(d_re, d_im, pf.Direction.Forward, planner)
+    # Parseval: sum|X|^2 = N sum|x|^2
+    e_x = float(np.sum(re0 * re0 + im0 * im0))
+    e_X = float((d_re.double().pow(2).sum() + d_im.double().pow(2).sum()).item())
+    assert abs(e_X / (n * e_x) - 1) < 1e-12
+    # DC bin = sum of the signal; a handful of bins against a direct f64 DFT sum
+    X_re = d_re.cpu().numpy(); X_im = d_im.cpu().numpy()
+    scale = np.sqrt(n)
+    assert abs(X_re[0] - re0.sum()) / scale < 1e-10 and abs(X_im[0] - im0.sum()) / scale < 1e-10
+    x = re0 + 1j * im0
+    for k in (1, 12345, n // 2, n - 1):
+        idx = (np.arange(n, dtype=np.int64) * k) % n
+        w = np.exp(-2j * np.pi * idx / n)
+        ref = np.sum(x * w)
+        assert abs((X_re[k] + 1j * X_im[k]) - ref) / scale < 1e-9, k
+    # oracle on the full size (a second or two on the host, multi-threaded)
+    o_re, o_im = re0.copy(), im0.copy()
+    O.fft_dit(o_re, o_im, O.FORWARD, parallel=True)
+    assert rel_linf(X_re, X_im, o_re, o_im) <= tol(np.float64, n)
+    del o_re, o_im
+    # round trip on the device
+    pf.fft_64_dit_with_planner(d_re, d_im, pf.Direction.Reverse, planner)
+    assert float((d_re - torch.from_numpy(re0).cuda()).abs().max().item()) < 1e-12
+    assert float((d_im - torch.from_numpy(im0).cuda()).abs().max().item()) < 1e-12
+
+
+def test_config_batch_f32_2pow16_linearity_and_oracle():
+    import torch
+    pf, O = _pf(), _O()
+    n, batch = 1 << 16, 256                        # a slice of the 4096-transform config (same kernels, same plan)
+    planner = pf.PlannerDit32(n)
+    rng = np.random.default_rng(1234)
+    a = rng.uniform(-1, 1, (2, batch * n)).astype(np.float32)
+    b = rng.uniform(-1, 1, (2, batch * n)).astype(np.float32)
+
+    def run(re, im):
+        d_re = torch.from_numpy(re.copy()).cuda(); d_im = torch.from_numpy(im.copy()).cuda()
+        pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, planner, batch)
+        return d_re.cpu().numpy(), d_im.cpu().numpy()
+
+    A = run(a[0], a[1]); B = run(b[0], b[1]); S = run(a[0] + b[0], a[1] + b[1])
+    lin = max(np.max(np.abs(S[0] - (A[0] + B[0]))), np.max(np.abs(S[1] - (A[1] + B[1]))))
+    assert lin / np.max(np.abs(S[0])) < 64 * np.finfo(np.float32).eps
+    for t in (0, 17, batch - 1):
+        s = slice(t * n, (t + 1) * n)
+        o_re, o_im = a[0][s].copy(), a[1][s].copy()
+        O.fft_dit(o_re, o_im, O.FORWARD)
+        assert rel_linf(A[0][s], A[1][s], o_re, o_im) <= tol(np.float32, n)
