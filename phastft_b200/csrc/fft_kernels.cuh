@@ -46,6 +46,9 @@ struct PassParams {
     int log2B;                     // B = stride of this pass's digit = product of later pass sizes
     int log2R1;                    // KIND_TRANS: size of the first pass digit (tile columns run over it)
     int log2Rprev;                 // size of the previous pass digit (0 if no inter-pass twiddle)
+    int blk_offset;                // KIND_COL: first linear tile index of this launch (L2-blocked sub-range of `a`)
+    int kt_base;                   // KIND_TRANS: first k1 tile of this launch ...
+    int log2_ktn;                  // ... and log2 of the number of k1 tiles it covers
     int has_tw;                    // apply inter-pass twiddle on load
     int tw_shift;                  // exponent scale: e_N = e_L << tw_shift   (N / L)
     Tw2 tw2;                       // two-level W_N table
@@ -85,7 +88,21 @@ struct TileAddr {
 // ---------------------------------------------------------------------------------------------
 // The pass kernel.
 // ---------------------------------------------------------------------------------------------
-template <typename T, class RL, int C, int NT, int KIND>
+// cp.async helpers (LDGSTS): global -> shared without staging through registers
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ASYNC = 1: stage 1 does not load global memory into registers; instead every thread fires
+// cp.async copies for the WHOLE tile straight into its (digit-reversed) shared-memory slots at
+// kernel entry, the inter-pass twiddle tables are built while those copies are in flight, and
+// stage 1 then runs out of shared memory like the later stages.  All of a CTA's input bytes are in
+// flight at once, independent of the register budget.
+template <typename T, class RL, int C, int NT, int KIND, int ASYNC = 0, int VARIANT = 0>
 struct PassKernel {
     static constexpr int S = RL::S;
     static constexpr int R = RL::R();
@@ -98,6 +115,7 @@ struct PassKernel {
     static constexpr int TILE_ELEMS = (S >= 2) ? R * C : 0;
     static constexpr int G_ELEMS = (KIND == KIND_TRANS) ? C * R1 : R1;
     static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)(TILE_ELEMS + M + G_ELEMS);
+    static_assert(!ASYNC || (S >= 2 && KIND != KIND_ROW), "the async variant needs a shared-memory tile");
 
     // ---- global element access -------------------------------------------------------------
     static __device__ __forceinline__ void gload(const PassParams<T>& p, long long idx, T& re, T& im) {
@@ -131,7 +149,8 @@ struct PassKernel {
         constexpr int TW_SHIFT = LOG2R - ilog2_c(NS * RAD);
         constexpr bool LAST = (s == S - 1);
         constexpr int NTASK = J * C;
-#pragma unroll 1
+        constexpr int TRIPS = (NTASK + NT - 1) / NT;
+#pragma unroll((VARIANT & 1) ? TRIPS : 1)
         for (int t = threadIdx.x; t < NTASK; t += NT) {
             int c, j;
             if constexpr (KIND == KIND_ROW) { j = t % J; c = t / J; } else { c = t % C; j = t / C; }
@@ -144,12 +163,28 @@ struct PassKernel {
                 cx<T> v = tile[Addr::at(base + i * NS, c)];
                 xr[i] = v.x; xi[i] = v.y;
             }
+            if constexpr ((VARIANT & 2) && RAD == 8) {
+                // 3 table loads (W^m, W^2m, W^4m), the other four twiddles by complex products
+                cx<T> w1 = __ldg(p.tw_stage + ((m * 1) << TW_SHIFT));
+                cx<T> w2 = __ldg(p.tw_stage + ((m * 2) << TW_SHIFT));
+                cx<T> w4 = __ldg(p.tw_stage + ((m * 4) << TW_SHIFT));
+                cx<T> w3 = cmul<T>(w1, w2), w5 = cmul<T>(w1, w4), w6 = cmul<T>(w2, w4);
+                cx<T> w7 = cmul<T>(w3, w4);
+                const cx<T> ws[8] = {w1, w1, w2, w3, w4, w5, w6, w7};
 #pragma unroll
-            for (int i = 1; i < RAD; ++i) {
-                cx<T> w = __ldg(p.tw_stage + ((m * i) << TW_SHIFT));
-                T a = xr[i], b = xi[i];
-                xr[i] = fma_t(-b, w.y, a * w.x);
-                xi[i] = fma_t(b, w.x, a * w.y);
+                for (int i = 1; i < RAD; ++i) {
+                    T a = xr[i], b = xi[i];
+                    xr[i] = fma_t(-b, ws[i].y, a * ws[i].x);
+                    xi[i] = fma_t(b, ws[i].x, a * ws[i].y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 1; i < RAD; ++i) {
+                    cx<T> w = __ldg(p.tw_stage + ((m * i) << TW_SHIFT));
+                    T a = xr[i], b = xi[i];
+                    xr[i] = fma_t(-b, w.y, a * w.x);
+                    xi[i] = fma_t(b, w.x, a * w.y);
+                }
             }
             Dft<T, RAD>::run(xr, xi);
             if constexpr (!LAST) {
@@ -197,8 +232,9 @@ struct PassKernel {
 
         if constexpr (KIND == KIND_COL) {
             const int tilesB = 1 << (p.log2B - LOG2C);
-            const int bt = blockIdx.x & (tilesB - 1);
-            const int rest = blockIdx.x >> (p.log2B - LOG2C);
+            const unsigned blk = blockIdx.x + (unsigned)p.blk_offset;
+            const int bt = blk & (tilesB - 1);
+            const int rest = blk >> (p.log2B - LOG2C);
             const int a = rest & ((1 << p.log2A) - 1);
             const int batch = rest >> p.log2A;
             const long long off = ((long long)a << (LOG2R + p.log2B)) + ((long long)bt << LOG2C);
@@ -212,9 +248,9 @@ struct PassKernel {
         } else if constexpr (KIND == KIND_TRANS) {
             // rows of the tile: a(c) = (k0 + c) * rest_n + rest, rest_n = A / R1
             const int log2restn = p.log2A - p.log2R1;
-            const int tilesK = 1 << (p.log2R1 - LOG2C);
-            const int kt = blockIdx.x & (tilesK - 1);
-            const int tmp = blockIdx.x >> (p.log2R1 - LOG2C);
+            const int tilesK = 1 << p.log2_ktn;
+            const int kt = p.kt_base + (blockIdx.x & (tilesK - 1));
+            const int tmp = blockIdx.x >> p.log2_ktn;
             const int rest = tmp & ((1 << log2restn) - 1);
             const int batch = tmp >> log2restn;
             const int k0 = kt << LOG2C;
@@ -235,6 +271,30 @@ struct PassKernel {
             in_rstride = 1;
             in_cstride = p.in_bstride;
             out_kstride = 1;
+        }
+
+        // ---- ASYNC: put the whole tile in flight before anything else --------------------------------
+        if constexpr (ASYNC) {
+            constexpr int NTASK0 = M * C;
+#pragma unroll 1
+            for (int t = tid; t < NTASK0; t += NT) {
+                int c, mp;
+                if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
+                const int j = rev_tail<RL>(mp);
+                const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
+#pragma unroll
+                for (int i = 0; i < R1; ++i) {
+                    const long long idx = a0 + (long long)(i * M) * in_rstride;
+                    cx<T>* dst = tile + Addr::at(j * R1 + i, c);
+                    if (p.in_interleaved) {
+                        cp_async<2 * (int)sizeof(T)>(dst, reinterpret_cast<const cx<T>*>(p.in_re) + idx);
+                    } else {
+                        cp_async<(int)sizeof(T)>(&dst->x, p.in_re + idx);
+                        cp_async<(int)sizeof(T)>(&dst->y, p.in_im + idx);
+                    }
+                }
+            }
+            cp_async_commit();
         }
 
         // ---- per-CTA inter-pass twiddle factors (two-level lookups, f64, once per CTA) ----------
@@ -261,19 +321,33 @@ struct PassKernel {
                 uint32_t e = kp0 * (bcol0 + (uint32_t)c);
                 vreg = to_cx<T>(p.tw2.get(e << p.tw_shift));
             }
+            if constexpr (!ASYNC) __syncthreads();
+        }
+        if constexpr (ASYNC) {
+            cp_async_wait_all();
             __syncthreads();
         }
 
         // ---- stage 1: global -> registers -> (twiddle, DFT) -> tile (or global when S == 1) ------
         {
             constexpr int NTASK = M * C;
-#pragma unroll 1
+            constexpr int TRIPS1 = (NTASK + NT - 1) / NT;
+#pragma unroll((VARIANT & 4) ? TRIPS1 : 1)
             for (int t = tid; t < NTASK; t += NT) {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
                 T xr[R1], xi[R1];
                 const bool valid = (KIND != KIND_ROW) || (c < rows_valid);
-                if (valid) {
+                if constexpr (ASYNC) {
+                    const int j0 = rev_tail<RL>(mp);
+                    const bool swap = p.in_interleaved == 2;
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) {
+                        cx<T> v = tile[Addr::at(j0 * R1 + i, c)];
+                        xr[i] = swap ? v.y : v.x;
+                        xi[i] = swap ? v.x : v.y;
+                    }
+                } else if (valid) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
 #pragma unroll
                     for (int i = 0; i < R1; ++i) gload(p, a0 + (long long)(i * M) * in_rstride, xr[i], xi[i]);
@@ -325,9 +399,9 @@ struct PassKernel {
     }
 };
 
-template <typename T, class RL, int C, int NT, int KIND>
-__global__ void __launch_bounds__(NT) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {
-    PassKernel<T, RL, C, NT, KIND>::body(p);
+template <typename T, class RL, int C, int NT, int KIND, int ASYNC, int VARIANT = 0, int MINB = 0>
+__global__ void __launch_bounds__(NT, MINB) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {
+    PassKernel<T, RL, C, NT, KIND, ASYNC, VARIANT>::body(p);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -70,38 +70,111 @@ struct DeviceGuard {
 // =================================================================================================
 template <typename T>
 struct KernelEntry {
-    int kind, R, C, NT, first_radix, stages;
+    int kind, R, C, NT, first_radix, stages, async, variant;
     size_t smem;
     const void* fn;
     std::string radices;
 };
 
-template <typename T, int KIND, int C, int NT, int... Rs>
-KernelEntry<T> make_entry() {
+// experimental variants (PHASTFT_VARIANT=<id> selects them; id 0 = the default kernels)
+template <typename T, int KIND, int C, int NT, int VARIANT, int MINB, int ID, int... Rs>
+KernelEntry<T> make_entry_v() {
     using RL = RadixList<Rs...>;
-    using PK = PassKernel<T, RL, C, NT, KIND>;
+    using PK = PassKernel<T, RL, C, NT, KIND, 0, VARIANT>;
+    KernelEntry<T> e;
+    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.async = 0; e.variant = ID;
+    e.smem = PK::SMEM_BYTES;
+    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, 0, VARIANT, MINB>);
+    const int rs[] = {Rs...};
+    for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
+    if (ID) e.radices += ",v" + std::to_string(ID);
+    return e;
+}
+
+template <typename T, int KIND, int C, int NT, int ASYNC, int... Rs>
+KernelEntry<T> make_entry_a() {
+    using RL = RadixList<Rs...>;
+    using PK = PassKernel<T, RL, C, NT, KIND, ASYNC>;
     static_assert(NT % 32 == 0, "whole warps");
     static_assert(KIND != KIND_COL || NT % C == 0, "a COL thread keeps its column");
     static_assert(PK::SMEM_BYTES <= 227 * 1024, "tile exceeds the 227 KB shared memory of an sm_100 CTA");
     KernelEntry<T> e;
-    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S;
+    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.async = ASYNC; e.variant = 0;
     e.smem = PK::SMEM_BYTES;
-    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND>);
+    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, ASYNC>);
     const int rs[] = {Rs...};
     for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
+    if (ASYNC) e.radices += ",async";
     return e;
+}
+template <typename T, int KIND, int C, int NT, int... Rs>
+KernelEntry<T> make_entry() { return make_entry_a<T, KIND, C, NT, 0, Rs...>(); }
+// register both the register-staged and the cp.async variant of a strided-kind kernel
+template <typename T, int KIND, int C, int NT, int... Rs>
+void add_both(std::vector<KernelEntry<T>>& v) {
+    v.push_back(make_entry_a<T, KIND, C, NT, 0, Rs...>());
+    v.push_back(make_entry_a<T, KIND, C, NT, 1, Rs...>());
 }
 
 // Tile width in columns for the strided (HBM-facing) kinds: C * sizeof(T) = 64 B (CN) or 128 B (CW).
 template <typename T> struct TileC;
-template <> struct TileC<double> { static constexpr int CN = 8, CW = 16; };
-template <> struct TileC<float> { static constexpr int CN = 16, CW = 32; };
+template <> struct TileC<double> { static constexpr int CH = 4, CN = 8, CW = 16; };
+template <> struct TileC<float> { static constexpr int CH = 8, CN = 16, CW = 32; };
+
+// The registry.  Every (kind, R, C) the planner can ask for has a DEFAULT entry (variant id 0) whose
+// code-generation knobs (task-loop unrolling, twiddle derivation, register budget, thread count) are
+// the ones that measured fastest on B200 for that tile (tools/tune*.py, profiles/r01_tuning.md);
+// the other ids are kept selectable (PHASTFT_VARIANT / PHASTFT_PASS_VARIANT) for re-tuning.
+//   knob bits: 1 = unroll the task loops of the shared-memory stages, 2 = stage twiddles from 3 table
+//   loads + products, 4 = unroll the stage-1 task loop;  MINB = CTAs/SM the register budget is sized for.
+template <typename T, int KIND>
+void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
+    constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
+    constexpr bool F64 = sizeof(T) == 8;
+    // ---- defaults -------------------------------------------------------------------------------------
+    v.push_back(make_entry_v<T, KIND, CN, 32, 0, 0, 0, 4, 8>());
+    v.push_back(make_entry_v<T, KIND, CW, 64, 0, 0, 0, 4, 8>());
+    v.push_back(make_entry_v<T, KIND, CN, 64, 0, 0, 0, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CW, 128, 0, 0, 0, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, 2 * CW, 256, 0, 0, 0, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 0, 16, 8>());
+    v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 8>());
+    v.push_back(make_entry_v<T, KIND, 2 * CW, 256, 0, 0, 0, 16, 8>());
+    if constexpr (F64) {
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 4, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 4, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());      // +20% over the plain build (tune5)
+        v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 0, 16, 8, 8>());
+    } else {
+        v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 0, 4, 8, 8>());      // f32: unrolled everywhere wins (tune6)
+        v.push_back(make_entry_v<T, KIND, CW, 256, 7, 2, 0, 4, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 0, 16, 8, 8>());
+    }
+    // ---- alternates kept for re-tuning ------------------------------------------------------------------
+    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 8, 8, 8>());          // id 1: plain build
+    v.push_back(make_entry_v<T, KIND, CN, 256, 2, 3, 2, 8, 8, 8>());          // id 2
+    v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 4, 8, 8, 8>());          // id 4
+    v.push_back(make_entry_v<T, KIND, CN, 512, 0, 2, 5, 8, 8, 8>());          // id 5: 512 threads
+    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 4, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CN, 256, 2, 3, 2, 4, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 4, 4, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CW, 256, 7, 2, 4, 4, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 16, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 20, 16, 8, 8>());        // id 20: 512 threads
+    v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 25, 8, 8, 16>());        // id 25
+}
 
 template <typename T>
 const std::vector<KernelEntry<T>>& registry() {
     static const std::vector<KernelEntry<T>> reg = [] {
         std::vector<KernelEntry<T>> v;
-        constexpr int CN = TileC<T>::CN, CW = TileC<T>::CW;
         // ---- whole transform in one CTA (rows contiguous in and out) -------------------------------
         v.push_back(make_entry<T, KIND_ROW, 64, 64, 2>());
         v.push_back(make_entry<T, KIND_ROW, 64, 64, 4>());
@@ -116,30 +189,9 @@ const std::vector<KernelEntry<T>>& registry() {
         v.push_back(make_entry<T, KIND_ROW, 1, 256, 4, 8, 8, 8>());
         v.push_back(make_entry<T, KIND_ROW, 1, 256, 8, 8, 8, 8>());
         if constexpr (sizeof(T) == 4) v.push_back(make_entry<T, KIND_ROW, 1, 512, 16, 8, 8, 8>());
-        // ---- first / middle passes (strided rows, contiguous C-element runs) -----------------------
-        v.push_back(make_entry<T, KIND_COL, CN, 32, 4, 8>());
-        v.push_back(make_entry<T, KIND_COL, CN, 64, 8, 8>());
-        v.push_back(make_entry<T, KIND_COL, CN, 128, 16, 8>());
-        v.push_back(make_entry<T, KIND_COL, CN, 256, 4, 8, 8>());
-        v.push_back(make_entry<T, KIND_COL, CN, 256, 8, 8, 8>());
-        v.push_back(make_entry<T, KIND_COL, CN, 256, 16, 8, 8>());
-        v.push_back(make_entry<T, KIND_COL, CW, 64, 4, 8>());
-        v.push_back(make_entry<T, KIND_COL, CW, 128, 8, 8>());
-        v.push_back(make_entry<T, KIND_COL, CW, 256, 16, 8>());
-        v.push_back(make_entry<T, KIND_COL, CW, 256, 4, 8, 8>());
-        v.push_back(make_entry<T, KIND_COL, CW, 256, 8, 8, 8>());
-        // ---- last pass of a multi-pass plan (contiguous rows in, transposed C-runs out) -------------
-        v.push_back(make_entry<T, KIND_TRANS, CN, 32, 4, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CN, 64, 8, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CN, 128, 16, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CN, 256, 4, 8, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CN, 256, 8, 8, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CN, 256, 16, 8, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CW, 64, 4, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CW, 128, 8, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CW, 256, 16, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CW, 256, 4, 8, 8>());
-        v.push_back(make_entry<T, KIND_TRANS, CW, 256, 8, 8, 8>());
+        // ---- first / middle passes (KIND_COL) and last pass (KIND_TRANS) ---------------------------
+        add_strided_kernels<T, KIND_COL>(v);
+        add_strided_kernels<T, KIND_TRANS>(v);
         return v;
     }();
     return reg;
@@ -215,6 +267,9 @@ struct Plan {
     mutable T* ws_re = nullptr;
     mutable T* ws_im = nullptr;
     mutable size_t ws_elems = 0;        // per array
+    T* ws2_re = nullptr;                // 3-pass plans: L2-resident scratch for one k1 group (see run_c2c)
+    T* ws2_im = nullptr;
+    long long l2_group = 0;             // k1 values per group
     mutable T* stage_re = nullptr;      // host-API staging (N each, or 2N for interleaved in stage_re)
     mutable T* stage_im = nullptr;
     mutable size_t stage_elems = 0;
@@ -229,6 +284,8 @@ struct Plan {
         if (blob_dev) cudaFree(blob_dev);
         if (ws_re) cudaFree(ws_re);
         if (ws_im) cudaFree(ws_im);
+        if (ws2_re) cudaFree(ws2_re);
+        if (ws2_im) cudaFree(ws2_im);
         if (stage_re) cudaFree(stage_re);
         if (stage_im) cudaFree(stage_im);
         if (ws_free) cudaEventDestroy(ws_free);
@@ -266,21 +323,55 @@ std::vector<int> choose_factors(int n) {
     }
     const int single_max = sizeof(T) == 8 ? 12 : 13;
     if (n <= single_max) return {n};
+    // two passes while both tiles stay <= 1024 points long; the ends of a 3-pass plan are kept at
+    // 2^8 so they can use 128-byte runs in a 64 KB tile, the middle pass takes the rest (<= 2^10)
+    // measured-best splits (tools/tune7.py, profiles/r01_tuning.md)
+    if (sizeof(T) == 4 && n == 16) return {7, 9};   // BASELINE configs[3] (batched 2^16 f32): 1.90 ms vs 2.09 ms for {8,8}
+    if (n <= 16) { int a = n / 2; return {a, n - a}; }
     if (n <= 20) { int a = (n + 1) / 2; return {a, n - a}; }
+    if (n <= 22) return {7, n - 14, 7};
+    if (n <= 26) return {8, n - 16, 8};
     int a = (n + 2) / 3, b = (n - a + 1) / 2;
-    return {a, b, n - a - b};
+    return {a, n - a - b, b};
 }
 
 template <typename T>
-const KernelEntry<T>* pick_kernel(int kind, int R, int max_c) {
-    int want_c = 0;
+const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bool hbm_strided) {
+    int want_c = 0, want_variant = 0;
+    auto nth = [&](const char* name, int& out) {
+        if (const char* env = getenv(name)) {
+            std::string sv(env);
+            size_t pos = 0;
+            for (int i = 0; pos <= sv.size(); ++i) {
+                size_t q = sv.find(',', pos);
+                if (q == std::string::npos) q = sv.size();
+                if (i == pass_index) out = atoi(sv.substr(pos, q - pos).c_str());
+                pos = q + 1;
+            }
+        }
+    };
     if (const char* env = getenv("PHASTFT_TILE_C")) want_c = atoi(env);
+    if (const char* env = getenv("PHASTFT_VARIANT")) want_variant = atoi(env);
+    nth("PHASTFT_PASS_C", want_c);                 // e.g. "16,8,16"
+    nth("PHASTFT_PASS_VARIANT", want_variant);     // e.g. "0,5,0"
+    const int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
+    const size_t tile_limit = 72 * 1024;           // keep >= 3 CTAs/SM worth of shared memory
     const KernelEntry<T>* best = nullptr;
+    int best_rank = 1 << 30;
     for (const auto& e : registry<T>()) {
         if (e.kind != kind || e.R != R) continue;
         if (kind != KIND_ROW && e.C > max_c) continue;
-        if (!best) best = &e;
-        if (want_c && e.C == want_c) { best = &e; break; }
+        if (e.variant != want_variant) continue;
+        int rank;
+        if (kind == KIND_ROW) rank = 0;
+        else if (want_c) rank = (e.C == want_c) ? 0 : 10 + abs(e.C - want_c);
+        else if (hbm_strided) rank = (e.C == CW && e.smem <= tile_limit) ? 0 : (e.C == CN) ? 1 : (e.C == CW) ? 2 : (e.C == CH) ? 4 : 3;
+        else rank = (e.C == CN) ? 0 : (e.C == CW && e.smem <= tile_limit) ? 1 : (e.C == CH) ? 2 : 3;
+        if (rank < best_rank) { best = &e; best_rank = rank; }
+    }
+    if (!best && want_variant != 0) {   // requested variant does not exist for this tile: fall back to the default
+        for (const auto& e : registry<T>())
+            if (e.kind == kind && e.R == R && e.variant == 0 && (kind == KIND_ROW || e.C <= max_c) && !best) best = &e;
     }
     return best;
 }
@@ -323,7 +414,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const bool last = (p == pl->num_passes - 1);
         const int kind = pl->num_passes == 1 ? KIND_ROW : (last ? KIND_TRANS : KIND_COL);
         const int max_c = kind == KIND_COL ? (1 << d.log2B) : kind == KIND_TRANS ? (1 << f[0]) : (1 << 30);
-        d.k = pick_kernel<T>(kind, 1 << f[p], max_c);
+        // wide (128-byte) runs pay off once the signal no longer lives in L2; below that more, smaller CTAs win
+        const bool big = n * 2 * sizeof(T) > (size_t(64) << 20);
+        const bool wide = (p == 0 || last) && (big || (sizeof(T) == 4 && ln == 16 && p == 0));
+        d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
         if (p > 0) {
             d.has_tw = 1;
@@ -377,6 +471,21 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         CUDA_TRY(cudaMalloc(&pl->ws_im, n * sizeof(T)));
         pl->ws_elems = n;
     }
+    if (pl->num_passes == 3) {
+        // L2 blocking of passes 2+3: group size in bytes from PHASTFT_L2_GROUP_MB (default 32; 0 disables)
+        size_t group_mb = 0;   // measured slower than three full-size passes (launch ramp/tail per group), off by default
+        if (const char* env = getenv("PHASTFT_L2_GROUP_MB")) group_mb = (size_t)atoi(env);
+        const size_t sub_bytes = (n >> f[0]) * 2 * sizeof(T);
+        const long long R1 = 1LL << f[0];
+        const long long ctrans = pl->pass[2].k->C;
+        long long G = ctrans;
+        while (G * 2 <= R1 && (size_t)(G * 2) * sub_bytes <= (group_mb << 20)) G *= 2;
+        if (group_mb > 0 && (size_t)G * sub_bytes * 2 <= n * 2 * sizeof(T)) {
+            pl->l2_group = G;
+            CUDA_TRY(cudaMalloc(&pl->ws2_re, (size_t)G * (n >> f[0]) * sizeof(T)));
+            CUDA_TRY(cudaMalloc(&pl->ws2_im, (size_t)G * (n >> f[0]) * sizeof(T)));
+        }
+    }
     // description
     {
         std::string s = "n=2^" + std::to_string(ln) + (sizeof(T) == 8 ? " f64:" : " f32:");
@@ -386,6 +495,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             s += std::string(p ? " |" : "") + " " + kind_name(k->kind) + " R=" + std::to_string(k->R) + "(" + k->radices + ") C=" +
                  std::to_string(k->C) + " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
         }
+        if (pl->l2_group) s += " | L2-blocked tail: " + std::to_string(pl->l2_group) + " k1/group";
         pl->description = s;
     }
     *out = pl.release();
@@ -403,8 +513,11 @@ struct Io {
     int in_il, out_il;   // 0 planar, 1 interleaved, 2 interleaved with re/im swapped
 };
 
+// k1_lo / k1_cnt (multi-pass plans, batch == 1): restrict a pass AFTER the first to the sub-transforms
+// whose first-pass output digit k1 lies in [k1_lo, k1_lo + k1_cnt) -- the unit of L2 blocking.
 template <typename T>
-int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, cudaStream_t stream) {
+int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, cudaStream_t stream,
+                    long long k1_lo = 0, long long k1_cnt = -1) {
     const PassDesc<T>& d = pl.pass[p];
     const KernelEntry<T>* k = d.k;
     PassParams<T> prm = base;
@@ -417,8 +530,20 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
     prm.tw_stage = reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_stage_off);
     prm.tw_wc = d.tw_wc_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_wc_off);
     unsigned long long blocks;
+    prm.blk_offset = 0; prm.kt_base = 0; prm.log2_ktn = d.log2R1 - ilog2(k->C);
     if (k->kind == KIND_ROW) blocks = (batch + k->C - 1) / k->C;
     else blocks = (unsigned long long)batch * (pl.n >> d.log2R) / k->C;
+    if (k1_cnt >= 0 && p > 0) {
+        const unsigned long long tiles_per_k1 = ((pl.n >> d.log2R) / k->C) >> d.log2R1;   // COL: (A/R1) * B/C
+        if (k->kind == KIND_COL) {
+            prm.blk_offset = (int)(k1_lo * tiles_per_k1);
+            blocks = k1_cnt * tiles_per_k1;
+        } else {
+            prm.kt_base = (int)(k1_lo / k->C);
+            prm.log2_ktn = ilog2((size_t)(k1_cnt / k->C));
+            blocks = ((pl.n >> d.log2R) >> d.log2R1) * (k1_cnt / k->C);                     // rest_n * chunk tiles
+        }
+    }
     if (blocks == 0 || blocks > 0x7fffffffULL) return fail(PHASTFT_ERR_INVALID_ARG, "grid too large");
     void* args[] = {&prm};
     CUDA_TRY(cudaLaunchKernel(k->fn, dim3((unsigned)blocks), dim3(k->NT), args, k->smem, stream));
@@ -428,7 +553,14 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
 
 // Bytes of intermediate (workspace) data we try to keep L2-resident when a batch is processed in
 // chunks: pass p writes the chunk's intermediate, pass p+1 reads it back before it is evicted.
-constexpr size_t L2_CHUNK_BYTES = 48u << 20;
+constexpr size_t L2_CHUNK_BYTES_DEFAULT = 48u << 20;
+inline size_t l2_chunk_bytes() {
+    static const size_t v = [] {
+        if (const char* env = getenv("PHASTFT_L2_CHUNK_MB")) { long mb = atol(env); if (mb > 0) return (size_t)mb << 20; }
+        return L2_CHUNK_BYTES_DEFAULT;
+    }();
+    return v;
+}
 
 // `pass_events` (profiling aid, bench.py roofline): if non-NULL, num_passes+1 events are recorded
 // around the passes of the FIRST chunk.
@@ -467,8 +599,9 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     // multi-pass: in -> ws (COL) [-> ws (COL)] -> out (TRANS), batch processed in L2-sized chunks
     std::lock_guard<std::mutex> lock(pl.mu);
     const size_t bytes_per = pl.n * 2 * sizeof(T);
-    size_t chunk = std::max<size_t>(1, L2_CHUNK_BYTES / bytes_per);
+    size_t chunk = std::max<size_t>(1, l2_chunk_bytes() / bytes_per);
     chunk = std::min(chunk, batch);
+    if (pl.num_passes == 3 && pl.ws2_re != nullptr) chunk = 1;
     if (pl.ws_elems < chunk * pl.n) {
         CUDA_TRY(cudaStreamSynchronize(stream));
         CUDA_TRY(cudaDeviceSynchronize());
@@ -488,6 +621,50 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     const bool capturing = cap != cudaStreamCaptureStatusNone;
     if (!capturing && pl.ws_last_stream != stream && pl.ws_used) CUDA_TRY(cudaStreamWaitEvent(stream, pl.ws_free, 0));
     const int P = pl.num_passes;
+    // ---- 3-pass plans: pass 1 streams the whole signal HBM -> HBM; passes 2+3 then run per group of
+    // G consecutive k1 values (G * N/R1 elements ~ tens of MiB): pass 2 writes its result into a small
+    // reused scratch that stays L2-resident and pass 3 reads it back from L2, so the tail costs one
+    // HBM read + one HBM write instead of two of each.
+    if (P == 3 && pl.ws2_re != nullptr) {
+        const long long R1 = 1LL << pl.pass[0].log2R;
+        const long long sub = (long long)(pl.n >> pl.pass[0].log2R);    // elements per k1
+        const long long G = pl.l2_group;
+        for (size_t b = 0; b < batch; ++b) {
+            memset(&prm, 0, sizeof(prm));
+            prm.scale = T(1);
+            prm.in_re = io.in_re + (io.in_il ? 2 : 1) * b * io.in_bstride;
+            prm.in_im = io.in_im ? io.in_im + b * io.in_bstride : nullptr;
+            prm.in_bstride = io.in_bstride; prm.in_interleaved = io.in_il;
+            prm.out_re = pl.ws_re; prm.out_im = pl.ws_im; prm.out_bstride = (long long)pl.n;
+            if (pass_events && b == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
+            int32_t st = launch_pass(pl, 0, prm, 1, stream);
+            if (st) return st;
+            if (pass_events && b == 0) CUDA_TRY(cudaEventRecord(pass_events[1], stream));
+            for (long long k1 = 0; k1 < R1; k1 += G) {
+                memset(&prm, 0, sizeof(prm));
+                prm.scale = T(1);
+                prm.in_re = pl.ws_re; prm.in_im = pl.ws_im; prm.in_bstride = (long long)pl.n;
+                prm.out_re = pl.ws2_re - k1 * sub; prm.out_im = pl.ws2_im - k1 * sub; prm.out_bstride = (long long)pl.n;
+                st = launch_pass(pl, 1, prm, 1, stream, k1, G);
+                if (st) return st;
+                memset(&prm, 0, sizeof(prm));
+                prm.in_re = pl.ws2_re - k1 * sub; prm.in_im = pl.ws2_im - k1 * sub; prm.in_bstride = (long long)pl.n;
+                prm.out_re = io.out_re + (io.out_il ? 2 : 1) * b * io.out_bstride;
+                prm.out_im = io.out_im ? io.out_im + b * io.out_bstride : nullptr;
+                prm.out_bstride = io.out_bstride; prm.out_interleaved = io.out_il;
+                prm.scale = scale;
+                st = launch_pass(pl, 2, prm, 1, stream, k1, G);
+                if (st) return st;
+            }
+            if (pass_events && b == 0) { CUDA_TRY(cudaEventRecord(pass_events[2], stream)); CUDA_TRY(cudaEventRecord(pass_events[3], stream)); }
+        }
+        if (!capturing) {
+            CUDA_TRY(cudaEventRecord(pl.ws_free, stream));
+            pl.ws_last_stream = stream;
+            pl.ws_used = true;
+        }
+        return PHASTFT_OK;
+    }
     for (size_t done = 0; done < batch; done += chunk) {
         const size_t nb = std::min(chunk, batch - done);
         for (int p = 0; p < P; ++p) {
