@@ -1,0 +1,222 @@
+//! PhastFT's public API, unchanged, over `libphastft_cuda.so` (B200 / sm_100a).
+//!
+//! Every item below keeps the name, signature and panic behaviour of the reference crate
+//! (QuState/PhastFT @ 8cd3a39; the `file:line` in each doc comment is the item it replaces), so a user
+//! switches by changing the dependency, not the call sites:
+//!
+//! ```ignore
+//! use phastft::{fft_64_dit, planner::Direction};
+//! let mut reals = vec![1.0, 0.0, 0.0, 0.0];
+//! let mut imags = vec![0.0; 4];
+//! fft_64_dit(&mut reals, &mut imags, Direction::Forward);   // runs on cuda:0
+//! ```
+//!
+//! The wrappers are deliberately thin: length checks that the reference performs with `assert!` happen
+//! inside the C ABI, which returns a status code; `check()` turns a non-zero code back into a `panic!`
+//! carrying the reference's message, so `#[should_panic(expected = "...")]` tests carry over.
+//! The device is chosen with the `PHASTFT_DEVICE` environment variable (default 0).
+pub mod ffi;
+pub mod options;
+pub mod planner;
+
+use options::Options;
+use planner::{Direction, PlannerDit32, PlannerDit64, PlannerR2c32, PlannerR2c64};
+
+/// Reference panic texts by status code (include/phastft_status.h).
+#[track_caller]
+pub(crate) fn check(code: i32) {
+    let msg = match code {
+        0 => return,
+        1 => "assertion `left == right` failed: reals.len() == imags.len()",
+        2 => "assertion failed: length must be a non-zero power of two",
+        3 => "assertion `left == right` failed: log_n == planner.log_n",
+        4 => "n must be a power of 2 >= 4",
+        5 => "input length must match planner size",
+        6 => "output_re must have length N/2 + 1",
+        7 => "output_im must have length N/2 + 1",
+        8 => "output length must match planner size",
+        9 => "input_re must have length N/2 + 1",
+        10 => "input_im must have length N/2 + 1",
+        11 => "scratch_re must have length N/2",
+        12 => "scratch_im must have length N/2",
+        _ => {
+            let detail = unsafe { std::ffi::CStr::from_ptr(ffi::phastft_last_error()) }.to_string_lossy().into_owned();
+            panic!("phastft_cuda error {code}: {detail}");
+        }
+    };
+    panic!("{msg}");
+}
+
+pub(crate) fn device() -> i32 {
+    std::env::var("PHASTFT_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0)
+}
+
+fn c_opts(o: &Options) -> ffi::phastft_options {
+    ffi::phastft_options {
+        multithreaded_bit_reversal: o.multithreaded_bit_reversal as i32,
+        smallest_parallel_chunk_size: o.smallest_parallel_chunk_size,
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// c2c, planar
+// ------------------------------------------------------------------------------------------------
+
+/// `algorithms/dit.rs:263` -- in place on planar slices; panics like the reference on length
+/// mismatch, non-power-of-two length, or a planner built for another size.
+pub fn fft_64_dit_with_planner_and_opts(reals: &mut [f64], imags: &mut [f64], direction: Direction, planner: &PlannerDit64, opts: &Options) {
+    let o = c_opts(opts);
+    check(unsafe {
+        ffi::phastft_fft_dit_f64_host(planner.raw, reals.as_mut_ptr(), reals.len(), imags.as_mut_ptr(), imags.len(), direction as i32, &o)
+    });
+}
+
+/// `algorithms/dit.rs:338`
+pub fn fft_32_dit_with_planner_and_opts(reals: &mut [f32], imags: &mut [f32], direction: Direction, planner: &PlannerDit32, opts: &Options) {
+    let o = c_opts(opts);
+    check(unsafe {
+        ffi::phastft_fft_dit_f32_host(planner.raw, reals.as_mut_ptr(), reals.len(), imags.as_mut_ptr(), imags.len(), direction as i32, &o)
+    });
+}
+
+/// `lib.rs:143`
+pub fn fft_64_dit_with_planner(reals: &mut [f64], imags: &mut [f64], direction: Direction, planner: &PlannerDit64) {
+    let opts = Options::guess_options(reals.len());
+    fft_64_dit_with_planner_and_opts(reals, imags, direction, planner, &opts);
+}
+
+/// `lib.rs:180` -- plans per call, like the reference.
+pub fn fft_64_dit(reals: &mut [f64], imags: &mut [f64], direction: Direction) {
+    let planner = PlannerDit64::new(reals.len());
+    fft_64_dit_with_planner(reals, imags, direction, &planner);
+}
+
+/// `lib.rs:186`
+pub fn fft_32_dit_with_planner(reals: &mut [f32], imags: &mut [f32], direction: Direction, planner: &PlannerDit32) {
+    let opts = Options::guess_options(reals.len());
+    fft_32_dit_with_planner_and_opts(reals, imags, direction, planner, &opts);
+}
+
+/// `lib.rs:223`
+pub fn fft_32_dit(reals: &mut [f32], imags: &mut [f32], direction: Direction) {
+    let planner = PlannerDit32::new(reals.len());
+    fft_32_dit_with_planner(reals, imags, direction, &planner);
+}
+
+// ------------------------------------------------------------------------------------------------
+// r2c / c2r  (algorithms/r2c.rs:521-895)
+// ------------------------------------------------------------------------------------------------
+
+/// `r2c.rs:535`
+pub fn r2c_fft_f64_with_planner(input_re: &[f64], output_re: &mut [f64], output_im: &mut [f64], planner: &PlannerR2c64) {
+    check(unsafe {
+        ffi::phastft_r2c_f64_host(planner.raw, input_re.as_ptr(), input_re.len(), output_re.as_mut_ptr(), output_re.len(),
+                                  output_im.as_mut_ptr(), output_im.len())
+    });
+}
+
+/// `r2c.rs:521`
+pub fn r2c_fft_f64(input_re: &[f64], output_re: &mut [f64], output_im: &mut [f64]) {
+    let planner = PlannerR2c64::new(input_re.len());
+    r2c_fft_f64_with_planner(input_re, output_re, output_im, &planner);
+}
+
+/// `r2c.rs:607`
+pub fn r2c_fft_f32_with_planner(input_re: &[f32], output_re: &mut [f32], output_im: &mut [f32], planner: &PlannerR2c32) {
+    check(unsafe {
+        ffi::phastft_r2c_f32_host(planner.raw, input_re.as_ptr(), input_re.len(), output_re.as_mut_ptr(), output_re.len(),
+                                  output_im.as_mut_ptr(), output_im.len())
+    });
+}
+
+/// `r2c.rs:598`
+pub fn r2c_fft_f32(input_re: &[f32], output_re: &mut [f32], output_im: &mut [f32]) {
+    let planner = PlannerR2c32::new(input_re.len());
+    r2c_fft_f32_with_planner(input_re, output_re, output_im, &planner);
+}
+
+/// `r2c.rs:740` -- caller scratch is length-checked like the reference; the work happens in device memory.
+pub fn c2r_fft_f64_with_planner_and_scratch(input_re: &[f64], input_im: &[f64], output: &mut [f64], planner: &PlannerR2c64,
+                                            scratch_re: &mut [f64], scratch_im: &mut [f64]) {
+    check(unsafe {
+        ffi::phastft_c2r_f64_host(planner.raw, input_re.as_ptr(), input_re.len(), input_im.as_ptr(), input_im.len(),
+                                  output.as_mut_ptr(), output.len(), scratch_re.as_mut_ptr(), scratch_re.len(),
+                                  scratch_im.as_mut_ptr(), scratch_im.len())
+    });
+}
+
+/// `r2c.rs:708` -- the reference allocates two N/2 Vecs here; the CUDA plan owns device scratch instead.
+pub fn c2r_fft_f64_with_planner(input_re: &[f64], input_im: &[f64], output: &mut [f64], planner: &PlannerR2c64) {
+    check(unsafe {
+        ffi::phastft_c2r_f64_host(planner.raw, input_re.as_ptr(), input_re.len(), input_im.as_ptr(), input_im.len(),
+                                  output.as_mut_ptr(), output.len(), std::ptr::null_mut(), 0, std::ptr::null_mut(), 0)
+    });
+}
+
+/// `r2c.rs:695`
+pub fn c2r_fft_f64(input_re: &[f64], input_im: &[f64], output: &mut [f64]) {
+    let planner = PlannerR2c64::new(output.len());
+    c2r_fft_f64_with_planner(input_re, input_im, output, &planner);
+}
+
+/// `r2c.rs:835`
+pub fn c2r_fft_f32_with_planner_and_scratch(input_re: &[f32], input_im: &[f32], output: &mut [f32], planner: &PlannerR2c32,
+                                            scratch_re: &mut [f32], scratch_im: &mut [f32]) {
+    check(unsafe {
+        ffi::phastft_c2r_f32_host(planner.raw, input_re.as_ptr(), input_re.len(), input_im.as_ptr(), input_im.len(),
+                                  output.as_mut_ptr(), output.len(), scratch_re.as_mut_ptr(), scratch_re.len(),
+                                  scratch_im.as_mut_ptr(), scratch_im.len())
+    });
+}
+
+/// `r2c.rs:813`
+pub fn c2r_fft_f32_with_planner(input_re: &[f32], input_im: &[f32], output: &mut [f32], planner: &PlannerR2c32) {
+    check(unsafe {
+        ffi::phastft_c2r_f32_host(planner.raw, input_re.as_ptr(), input_re.len(), input_im.as_ptr(), input_im.len(),
+                                  output.as_mut_ptr(), output.len(), std::ptr::null_mut(), 0, std::ptr::null_mut(), 0)
+    });
+}
+
+/// `r2c.rs:804`
+pub fn c2r_fft_f32(input_re: &[f32], input_im: &[f32], output: &mut [f32]) {
+    let planner = PlannerR2c32::new(output.len());
+    c2r_fft_f32_with_planner(input_re, input_im, output, &planner);
+}
+
+// ------------------------------------------------------------------------------------------------
+// interleaved Complex<T> API (lib.rs:41-140, feature `complex-nums`)
+// ------------------------------------------------------------------------------------------------
+#[cfg(feature = "complex-nums")]
+mod interleaved {
+    use super::*;
+    use num_complex::Complex;
+
+    /// `lib.rs:41-60`: the reference deinterleaves into two Vecs, transforms, re-interleaves; here the
+    /// AoS <-> planar conversion is fused into the first pass's load and the last pass's store.
+    pub fn fft_64_interleaved_with_planner_and_opts(signal: &mut [Complex<f64>], direction: Direction, planner: &PlannerDit64, _opts: &Options) {
+        check(unsafe { ffi::phastft_fft_interleaved_f64_host(planner.raw, signal.as_mut_ptr() as *mut f64, signal.len(), direction as i32) });
+    }
+    pub fn fft_32_interleaved_with_planner_and_opts(signal: &mut [Complex<f32>], direction: Direction, planner: &PlannerDit32, _opts: &Options) {
+        check(unsafe { ffi::phastft_fft_interleaved_f32_host(planner.raw, signal.as_mut_ptr() as *mut f32, signal.len(), direction as i32) });
+    }
+    /// `lib.rs:77-97`
+    pub fn fft_64_interleaved_with_planner(signal: &mut [Complex<f64>], direction: Direction, planner: &PlannerDit64) {
+        let opts = Options::guess_options(signal.len());
+        fft_64_interleaved_with_planner_and_opts(signal, direction, planner, &opts);
+    }
+    pub fn fft_32_interleaved_with_planner(signal: &mut [Complex<f32>], direction: Direction, planner: &PlannerDit32) {
+        let opts = Options::guess_options(signal.len());
+        fft_32_interleaved_with_planner_and_opts(signal, direction, planner, &opts);
+    }
+    /// `lib.rs:113-140`
+    pub fn fft_64_interleaved(signal: &mut [Complex<f64>], direction: Direction) {
+        let planner = PlannerDit64::new(signal.len());
+        fft_64_interleaved_with_planner(signal, direction, &planner);
+    }
+    pub fn fft_32_interleaved(signal: &mut [Complex<f32>], direction: Direction) {
+        let planner = PlannerDit32::new(signal.len());
+        fft_32_interleaved_with_planner(signal, direction, &planner);
+    }
+}
+#[cfg(feature = "complex-nums")]
+pub use interleaved::*;
