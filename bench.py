@@ -113,7 +113,12 @@ def cpu_reference_run(workload: str, steps: int, warmup: int, budget_s: float):
     (examples/benchmark.rs:42-63: planner reused, fresh random unit-norm signal per iteration,
     wall clock around exactly one in-place FFT, median).  Returns (value, unit, info dict)."""
     from oracle import oracle as O
-    threads = O.max_threads()
+    # all host threads the process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm ignores that)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    O.set_threads(threads)
     if workload == "batch_f32":
         n, dt = 1 << 16, np.float32
     elif workload == "c2c_f64_2p26":
@@ -405,7 +410,7 @@ def run_ours(args):
         # algorithmic bytes of ONE launch: it reads each planar array of its chunk once and writes it once
         chunk = batch_
         if batch_ > 1:
-            chunk = max(1, min(batch_, (48 << 20) // (n_ * 2 * esz)))
+            chunk = max(1, min(batch_, (4 << 30) // (n_ * 2 * esz)))
         bytes_launch = 2 * n_ * esz * 2 * chunk
         ach = bytes_launch / (avg[dom] * 1e-3) / 1e9
         traffic = None

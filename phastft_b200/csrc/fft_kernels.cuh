@@ -49,6 +49,7 @@ struct PassParams {
     int blk_offset;                // KIND_COL: first linear tile index of this launch (L2-blocked sub-range of `a`)
     int kt_base;                   // KIND_TRANS: first k1 tile of this launch ...
     int log2_ktn;                  // ... and log2 of the number of k1 tiles it covers
+    int pdl;                       // launched with programmatic stream serialization
     int has_tw;                    // apply inter-pass twiddle on load
     int tw_shift;                  // exponent scale: e_N = e_L << tw_shift   (N / L)
     Tw2 tw2;                       // two-level W_N table
@@ -222,6 +223,13 @@ struct PassKernel {
         cx<T>* s_g = s_um + M;             // [C][R1] or [R1]     W_L^(kp(c)*M*B*i)
 
         const int tid = threadIdx.x;
+        // Programmatic dependent launch (sm_90+): this grid may have been scheduled while the previous
+        // pass is still draining; wait for its memory to be visible before touching global data, and
+        // let the next pass's CTAs be scheduled as soon as every CTA of this grid is resident.
+        if (p.pdl) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            asm volatile("griddepcontrol.launch_dependents;");
+        }
         long long in_base, out_base, out_kstride;
         long long in_rstride;          // element stride of the tile row index r (COL) / 1 (ROW, TRANS)
         long long in_cstride;          // element stride between tile columns

@@ -140,17 +140,19 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 0, 16, 8>());
     v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 8>());
     v.push_back(make_entry_v<T, KIND, 2 * CW, 256, 0, 0, 0, 16, 8>());
+    // R = 256 as two radix-16 stages (one shared-memory exchange): 5.5 TB/s as a first pass vs 4.25 TB/s for
+    // 4x8x8 (tune9/tune10); 128 threads for the 64-byte-run f64 tile (128 tasks per stage)
     if constexpr (F64) {
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 4, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 4, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 0, 16, 16>());
+        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 16>());
         v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());      // +20% over the plain build (tune5)
         v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 0, 16, 8, 8>());     // 512 threads: 20.0 vs 21.2 us at 2^20 (tune8)
         v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 0, 16, 8, 8>());
     } else {
-        v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 0, 4, 8, 8>());      // f32: unrolled everywhere wins (tune6)
-        v.push_back(make_entry_v<T, KIND, CW, 256, 7, 2, 0, 4, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 16, 16>());
+        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 16>());
         v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
@@ -163,11 +165,12 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 4, 8, 8, 8>());          // id 4
     v.push_back(make_entry_v<T, KIND, CN, 512, 0, 2, 5, 8, 8, 8>());          // id 5: 512 threads
     v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 4, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 1, 4, 8, 8>());
     v.push_back(make_entry_v<T, KIND, CN, 256, 2, 3, 2, 4, 8, 8>());
     v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 4, 4, 8, 8>());
     v.push_back(make_entry_v<T, KIND, CW, 256, 7, 2, 4, 4, 8, 8>());
     v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 16, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 20, 16, 8, 8>());        // id 20: 512 threads
+    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 20, 16, 8, 8>());        // id 20: 256 threads
     v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 25, 8, 8, 16>());        // id 25
 }
 
@@ -326,7 +329,6 @@ std::vector<int> choose_factors(int n) {
     // two passes while both tiles stay <= 1024 points long; the ends of a 3-pass plan are kept at
     // 2^8 so they can use 128-byte runs in a 64 KB tile, the middle pass takes the rest (<= 2^10)
     // measured-best splits (tools/tune7.py, profiles/r01_tuning.md)
-    if (sizeof(T) == 4 && n == 16) return {7, 9};   // BASELINE configs[3] (batched 2^16 f32): 1.90 ms vs 2.09 ms for {8,8}
     if (n <= 16) { int a = n / 2; return {a, n - a}; }
     if (n <= 20) { int a = (n + 1) / 2; return {a, n - a}; }
     if (n <= 22) return {7, n - 14, 7};
@@ -416,7 +418,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const int max_c = kind == KIND_COL ? (1 << d.log2B) : kind == KIND_TRANS ? (1 << f[0]) : (1 << 30);
         // wide (128-byte) runs pay off once the signal no longer lives in L2; below that more, smaller CTAs win
         const bool big = n * 2 * sizeof(T) > (size_t(64) << 20);
-        const bool wide = (p == 0 || last) && (big || (sizeof(T) == 4 && ln == 16 && p == 0));
+        const bool wide = (p == 0 || last) && big;
         d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
         if (p > 0) {
@@ -546,14 +548,31 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
     }
     if (blocks == 0 || blocks > 0x7fffffffULL) return fail(PHASTFT_ERR_INVALID_ARG, "grid too large");
     void* args[] = {&prm};
-    CUDA_TRY(cudaLaunchKernel(k->fn, dim3((unsigned)blocks), dim3(k->NT), args, k->smem, stream));
+    static const bool use_pdl = [] { const char* e = getenv("PHASTFT_PDL"); return e ? atoi(e) != 0 : false; }();   // measured: no gain at 2^20, -10% at 2^24+ (tune8)
+    if (use_pdl) {
+        // Programmatic dependent launch: back-to-back passes overlap the next grid's launch and prologue
+        // with the previous grid's tail (the kernel waits with griddepcontrol.wait before its first access).
+        prm.pdl = 1;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(k->NT); cfg.dynamicSmemBytes = k->smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, k->fn, args));
+    } else {
+        CUDA_TRY(cudaLaunchKernel(k->fn, dim3((unsigned)blocks), dim3(k->NT), args, k->smem, stream));
+    }
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return PHASTFT_OK;
 }
 
-// Bytes of intermediate (workspace) data we try to keep L2-resident when a batch is processed in
-// chunks: pass p writes the chunk's intermediate, pass p+1 reads it back before it is evicted.
-constexpr size_t L2_CHUNK_BYTES_DEFAULT = 48u << 20;
+// A batch is processed in chunks so the workspace stays bounded.  Measured on B200 (tools/tune12.py):
+// keeping a chunk's intermediate L2-resident (48 MiB chunks) is SLOWER than few large launches --
+// 4096 x 2^16 f32: 1.88 ms at 48 MiB, 1.61 ms at 192 MiB, 1.50 ms unchunked -- so the default chunk is
+// as large as the workspace cap allows (PHASTFT_L2_CHUNK_MB overrides).
+constexpr size_t L2_CHUNK_BYTES_DEFAULT = size_t(4) << 30;
 inline size_t l2_chunk_bytes() {
     static const size_t v = [] {
         if (const char* env = getenv("PHASTFT_L2_CHUNK_MB")) { long mb = atol(env); if (mb > 0) return (size_t)mb << 20; }

@@ -30,7 +30,7 @@ def prof(sfx, n_log, env, batch=1, reps=10):
             for i in range(npass.value):
                 acc[i] += ms[i] / reps
     esz = 8 if sfx == "f64" else 4
-    chunk = batch if batch == 1 else max(1, min(batch, (48 << 20) // (n * 2 * esz)))
+    chunk = batch if batch == 1 else max(1, min(batch, (4 << 30) // (n * 2 * esz)))
     gb = 2 * n * esz * 2 * chunk / 1e9
     parts = "  ".join(f"p{i+1} {acc[i]*1e3:8.1f} us {gb/(acc[i]*1e-3)/1e3:5.2f} TB/s" for i in range(npass.value))
     print(f"{sfx} 2^{n_log} {env}: total {sum(acc)*1e3:8.1f} us | {parts} | {pl.describe()[:230]}", flush=True)
