@@ -220,7 +220,7 @@ def run_reference(args):
 
 
 def planner_passes(planner) -> int:
-    return planner.describe().count("|") + 1
+    return planner.describe().split(" || ")[0].count(" | ") + 1
 
 
 def workload_config(workload: str, gpus: int):

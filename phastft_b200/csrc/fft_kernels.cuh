@@ -305,6 +305,27 @@ struct PassKernel {
             cp_async_commit();
         }
 
+        // ---- PRELOAD: when every thread owns exactly one stage-1 task, issue its global loads NOW so
+        // they are in flight while the twiddle tables below are built (their two-level lookups are two
+        // dependent L2 round trips that would otherwise sit in front of the first data load).
+        constexpr bool PRELOAD = !ASYNC && (M * C <= NT);
+        T pre_r[PRELOAD ? R1 : 1], pre_i[PRELOAD ? R1 : 1];
+        if constexpr (PRELOAD) {
+            const int t = tid;
+            if (t < M * C) {
+                int c, mp;
+                if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
+                if ((KIND != KIND_ROW) || (c < rows_valid)) {
+                    const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) gload(p, a0 + (long long)(i * M) * in_rstride, pre_r[i], pre_i[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) { pre_r[i] = T(0); pre_i[i] = T(0); }
+                }
+            }
+        }
+
         // ---- per-CTA inter-pass twiddle factors (two-level lookups, f64, once per CTA) ----------
         // tw(r, c) = W_L^( kp(c) * (r*B + bcol(c)) ),  r = m' + i*M
         //          = W_L^(kp*B*m') * W_L^(kp*bcol) * W_L^(kp*M*B*i)  =  Um[m'] * V[c] * G[c][i]
@@ -355,6 +376,9 @@ struct PassKernel {
                         xr[i] = swap ? v.y : v.x;
                         xi[i] = swap ? v.x : v.y;
                     }
+                } else if constexpr (PRELOAD) {
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) { xr[i] = pre_r[i]; xi[i] = pre_i[i]; }
                 } else if (valid) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
 #pragma unroll

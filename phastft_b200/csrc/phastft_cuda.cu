@@ -132,6 +132,9 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
     constexpr bool F64 = sizeof(T) == 8;
     // ---- defaults -------------------------------------------------------------------------------------
+    v.push_back(make_entry_v<T, KIND, CH, 32, 0, 0, 0, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CH, 64, 0, 0, 0, 16, 8>());
+    v.push_back(make_entry_v<T, KIND, CH, F64 ? 64 : 128, 0, 0, 0, 16, 16>());
     v.push_back(make_entry_v<T, KIND, CN, 32, 0, 0, 0, 4, 8>());
     v.push_back(make_entry_v<T, KIND, CW, 64, 0, 0, 0, 4, 8>());
     v.push_back(make_entry_v<T, KIND, CN, 64, 0, 0, 0, 8, 8>());
@@ -149,15 +152,18 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
         v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 0, 16, 8, 8>());     // 512 threads: 20.0 vs 21.2 us at 2^20 (tune8)
-        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 512, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 60, 16, 8, 8>());
     } else {
         v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 16, 16>());
         v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 16>());
         v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 60, 16, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 512, 0, 1, 60, 16, 8, 8>());
     }
     // ---- alternates kept for re-tuning ------------------------------------------------------------------
     v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 8, 8, 8>());          // id 1: plain build
@@ -192,6 +198,11 @@ const std::vector<KernelEntry<T>>& registry() {
         v.push_back(make_entry<T, KIND_ROW, 1, 256, 4, 8, 8, 8>());
         v.push_back(make_entry<T, KIND_ROW, 1, 256, 8, 8, 8, 8>());
         if constexpr (sizeof(T) == 4) v.push_back(make_entry<T, KIND_ROW, 1, 512, 16, 8, 8, 8>());
+        v.push_back(make_entry_v<T, KIND_ROW, 1, 256, 0, 0, 70, 16, 16, 16>());
+        v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 70, 8, 16, 16>());
+        v.push_back(make_entry_v<T, KIND_ROW, 1, 64, 0, 0, 70, 4, 16, 16>());
+        v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 70, 16, 16>());
+
         // ---- first / middle passes (KIND_COL) and last pass (KIND_TRANS) ---------------------------
         add_strided_kernels<T, KIND_COL>(v);
         add_strided_kernels<T, KIND_TRANS>(v);
@@ -244,13 +255,16 @@ void root_of_unity(uint64_t k, uint64_t n, double& re, double& im) {
 // plans
 // =================================================================================================
 constexpr int MAX_PASSES = 3;
+constexpr int ALT_ROW_PASS = -1;   // launch_pass(): use Plan::alt_row
 
 template <typename T>
 struct PassDesc {
-    const KernelEntry<T>* k = nullptr;
+    const KernelEntry<T>* k = nullptr;    // kernel for a lone transform
+    const KernelEntry<T>* kb = nullptr;   // kernel when the call carries many transforms (multi-wave grids)
     int log2R = 0, log2A = 0, log2B = 0, log2R1 = 0, log2Rprev = 0, has_tw = 0, tw_shift = 0;
     size_t tw_stage_off = 0;  // byte offsets into the table blob
     size_t tw_wc_off = (size_t)-1;
+    size_t tw_wc_off_b = (size_t)-1;      // same table for `kb` (depends on its C and first radix)
 };
 
 template <typename T>
@@ -260,6 +274,7 @@ struct Plan {
     int device = 0;
     int num_passes = 0;
     PassDesc<T> pass[MAX_PASSES];
+    PassDesc<T> alt_row;               // N <= 4096 planned as two passes: the one-CTA kernel, used for batches
     // table blob: [tw2_hi][tw2_lo][per pass W_R][wc]
     std::vector<unsigned char> blob_host;
     unsigned char* blob_dev = nullptr;
@@ -324,7 +339,10 @@ std::vector<int> choose_factors(int n) {
             pos = end + 1;
         }
     }
-    const int single_max = sizeof(T) == 8 ? 12 : 13;
+    // A lone transform is one CTA only while that beats two many-CTA passes (tools/tune17.py: f64 2^12
+    // 7.9 us in one CTA vs 4.9 us as {6,6}; f32 2^12 5.6 vs 5.9 us).  Batches of <= 2^12-point transforms
+    // always use the one-CTA kernel (Plan::alt_row): one launch, one HBM round trip.
+    const int single_max = sizeof(T) == 8 ? 10 : 12;
     if (n <= single_max) return {n};
     // two passes while both tiles stay <= 1024 points long; the ends of a 3-pass plan are kept at
     // 2^8 so they can use 128-byte runs in a 64 KB tile, the middle pass takes the rest (<= 2^10)
@@ -337,8 +355,13 @@ std::vector<int> choose_factors(int n) {
     return {a, n - a - b, b};
 }
 
+// `l2_resident`: the whole signal fits L2 (a few MiB .. 64 MiB).  There the passes are launch- and
+// latency-bound single waves and the tile width is chosen by a wave model (tools/tune15.py, tune16.py:
+// 2^18 f64 8.8 us with 4-column tiles vs 12.2 us with 8; 2^20 f32 16.6 us with 8 columns vs 25.4 us
+// with 16; 2^20 f64 stays at 8 columns because its 1024-row tile holds only one CTA per SM).
 template <typename T>
-const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bool hbm_strided) {
+const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bool hbm_strided, bool l2_resident = false,
+                                  size_t rows_total = 0) {
     int want_c = 0, want_variant = 0;
     auto nth = [&](const char* name, int& out) {
         if (const char* env = getenv(name)) {
@@ -367,6 +390,19 @@ const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bo
         int rank;
         if (kind == KIND_ROW) rank = 0;
         else if (want_c) rank = (e.C == want_c) ? 0 : 10 + abs(e.C - want_c);
+        else if (l2_resident) {
+            // cost ~ (waves of CTAs) x (points per tile): a pass over an L2-resident signal is one or two
+            // latency-bound waves, so smaller tiles win until they no longer fit the chip in one wave
+            if (e.C != CH && e.C != CN && e.C != CW) continue;
+            int occ = 1, sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaFuncSetAttribute(e.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e.smem);
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, e.fn, e.NT, e.smem) != cudaSuccess || occ < 1) occ = 1;
+            const size_t ctas = std::max<size_t>(1, rows_total / (size_t)e.C);
+            const size_t waves = (ctas + (size_t)sms * occ - 1) / ((size_t)sms * occ);
+            rank = (int)std::min<size_t>(waves * (size_t)e.R * e.C, 1u << 24) * 4 - ilog2(e.C);   // tie -> wider tile
+        }
         else if (hbm_strided) rank = (e.C == CW && e.smem <= tile_limit) ? 0 : (e.C == CN) ? 1 : (e.C == CW) ? 2 : (e.C == CH) ? 4 : 3;
         else rank = (e.C == CN) ? 0 : (e.C == CW && e.smem <= tile_limit) ? 1 : (e.C == CH) ? 2 : 3;
         if (rank < best_rank) { best = &e; best_rank = rank; }
@@ -376,6 +412,17 @@ const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bo
             if (e.kind == kind && e.R == R && e.variant == 0 && (kind == KIND_ROW || e.C <= max_c) && !best) best = &e;
     }
     return best;
+}
+
+// One-CTA kernels: for a batch the radix-16 builds win at some sizes (tools/tune19.py: 2^8 6.7 vs 4.5 TB/s,
+// f32 2^11 3.4 vs 2.2 TB/s, f64 2^11/2^12 3.4 vs 2.9 TB/s) while a lone transform prefers the default.
+template <typename T>
+const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
+    const bool use16 = R == 256 || R == 2048 || (R == 4096 && sizeof(T) == 8);
+    if (!use16) return dflt;
+    for (const auto& e : registry<T>())
+        if (e.kind == KIND_ROW && e.R == R && e.variant == 70) return &e;
+    return dflt;
 }
 
 template <typename T>
@@ -417,9 +464,14 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const int kind = pl->num_passes == 1 ? KIND_ROW : (last ? KIND_TRANS : KIND_COL);
         const int max_c = kind == KIND_COL ? (1 << d.log2B) : kind == KIND_TRANS ? (1 << f[0]) : (1 << 30);
         // wide (128-byte) runs pay off once the signal no longer lives in L2; below that more, smaller CTAs win
-        const bool big = n * 2 * sizeof(T) > (size_t(64) << 20);
+        const bool big = ln >= 21;     // above 2^20 the passes are multi-wave streams, below single latency-bound waves
         const bool wide = (p == 0 || last) && big;
-        d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide);
+        d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide, /*l2_resident=*/!big, /*rows_total=*/n >> f[p]);
+        // batched calls are multi-wave streams whatever N is: wide runs only where the rows of a tile are
+        // far apart in memory (>= 64 KiB: first-pass loads, last-pass stores of large N), else 64-byte runs
+        const size_t far_stride = (kind == KIND_COL ? (size_t(1) << d.log2B) : (n >> f[p])) * sizeof(T);
+        const bool wide_b = (p == 0 || last) && far_stride >= (size_t(64) << 10);
+        d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
         if (p > 0) {
             d.has_tw = 1;
@@ -430,8 +482,26 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         if (kind == KIND_TRANS && pl->num_passes == 2) {
             d.tw_wc_off = off;
             off += (size_t)d.k->C * ((size_t(1) << f[p]) / d.k->first_radix) * sizeof(cx<T>);
+            if (d.kb && d.kb != d.k) {
+                off = (off + 255) & ~size_t(255);
+                d.tw_wc_off_b = off;
+                off += (size_t)d.kb->C * ((size_t(1) << f[p]) / d.kb->first_radix) * sizeof(cx<T>);
+            } else {
+                d.tw_wc_off_b = d.tw_wc_off;
+            }
         }
         off = (off + 255) & ~size_t(255);
+    }
+    if (pl->num_passes >= 2 && ln <= 12) {
+        PassDesc<T>& d = pl->alt_row;
+        d.log2R = ln; d.log2A = 0; d.log2B = 0; d.log2R1 = ln;
+        d.k = pick_kernel<T>(KIND_ROW, 1 << ln, 1 << 30, 0, false);
+        if (d.k) d.k = pick_row_batch_kernel<T>(1 << ln, d.k);   // alt_row is only ever used for batches
+        d.kb = d.k;
+        if (d.k) {
+            d.tw_stage_off = off; off += (size_t(1) << ln) * sizeof(cx<T>);
+            off = (off + 255) & ~size_t(255);
+        }
     }
     // ---- fill the blob ------------------------------------------------------------------------------
     pl->blob_host.assign(off ? off : 256, 0);
@@ -450,11 +520,14 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             root_of_unity(e, R, re, im);
             tw[e].x = (T)re; tw[e].y = (T)im;
         }
-        if (d.tw_wc_off != (size_t)-1) {
+        for (int which = 0; which < 2; ++which) {
+            const KernelEntry<T>* kk = which ? d.kb : d.k;
+            const size_t woff = which ? d.tw_wc_off_b : d.tw_wc_off;
+            if (woff == (size_t)-1 || (which && woff == d.tw_wc_off)) continue;
             // W_L^(c*m), L = N (2-pass plan), [c][m] layout, m < M = R / first_radix
-            const size_t M = R / d.k->first_radix;
-            cx<T>* wc = reinterpret_cast<cx<T>*>(pl->blob_host.data() + d.tw_wc_off);
-            for (int c = 0; c < d.k->C; ++c)
+            const size_t M = R / kk->first_radix;
+            cx<T>* wc = reinterpret_cast<cx<T>*>(pl->blob_host.data() + woff);
+            for (int c = 0; c < kk->C; ++c)
                 for (size_t m = 0; m < M; ++m) {
                     double re, im;
                     root_of_unity((uint64_t)c * m, n, re, im);
@@ -462,12 +535,26 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                 }
         }
     }
+    if (pl->alt_row.k) {
+        const size_t R = size_t(1) << pl->alt_row.log2R;
+        cx<T>* tw = reinterpret_cast<cx<T>*>(pl->blob_host.data() + pl->alt_row.tw_stage_off);
+        for (size_t e = 0; e < R; ++e) {
+            double re, im;
+            root_of_unity(e, R, re, im);
+            tw[e].x = (T)re; tw[e].y = (T)im;
+        }
+    }
     CUDA_TRY(cudaMalloc(&pl->blob_dev, pl->blob_host.size()));
     CUDA_TRY(cudaMemcpy(pl->blob_dev, pl->blob_host.data(), pl->blob_host.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&pl->ws_free, cudaEventDisableTiming));
-    for (int p = 0; p < pl->num_passes; ++p)
+    for (int p = 0; p < pl->num_passes; ++p) {
         CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].k->smem));
+        if (pl->pass[p].kb)
+            CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kb->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kb->smem));
+    }
+    if (pl->alt_row.k)
+        CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.k->smem));
     if (pl->num_passes >= 2) {
         CUDA_TRY(cudaMalloc(&pl->ws_re, n * sizeof(T)));
         CUDA_TRY(cudaMalloc(&pl->ws_im, n * sizeof(T)));
@@ -498,6 +585,17 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                  std::to_string(k->C) + " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
         }
         if (pl->l2_group) s += " | L2-blocked tail: " + std::to_string(pl->l2_group) + " k1/group";
+        bool differs = false;
+        for (int p = 0; p < pl->num_passes; ++p) differs |= pl->pass[p].kb && pl->pass[p].kb != pl->pass[p].k;
+        if (differs) {
+            s += " || batches:";
+            for (int p = 0; p < pl->num_passes; ++p) {
+                const auto* k = pl->pass[p].kb;
+                s += std::string(p ? " |" : "") + " " + kind_name(k->kind) + " R=" + std::to_string(k->R) + "(" + k->radices + ") C=" +
+                     std::to_string(k->C) + " NT=" + std::to_string(k->NT);
+            }
+        }
+        if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
         pl->description = s;
     }
     *out = pl.release();
@@ -520,8 +618,9 @@ struct Io {
 template <typename T>
 int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, cudaStream_t stream,
                     long long k1_lo = 0, long long k1_cnt = -1) {
-    const PassDesc<T>& d = pl.pass[p];
-    const KernelEntry<T>* k = d.k;
+    const PassDesc<T>& d = (p == ALT_ROW_PASS) ? pl.alt_row : pl.pass[p];
+    const bool many = d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
+    const KernelEntry<T>* k = many ? d.kb : d.k;
     PassParams<T> prm = base;
     prm.batch = (int)batch;
     prm.log2A = d.log2A; prm.log2B = d.log2B; prm.log2R1 = d.log2R1; prm.log2Rprev = d.log2Rprev;
@@ -530,7 +629,8 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
     prm.tw2.lo = reinterpret_cast<const double2*>(pl.blob_dev + pl.lo_off);
     prm.tw2.lo_bits = pl.lo_bits;
     prm.tw_stage = reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_stage_off);
-    prm.tw_wc = d.tw_wc_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_wc_off);
+    const size_t wc_off = many ? d.tw_wc_off_b : d.tw_wc_off;
+    prm.tw_wc = wc_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + wc_off);
     unsigned long long blocks;
     prm.blk_offset = 0; prm.kt_base = 0; prm.log2_ktn = d.log2R1 - ilog2(k->C);
     if (k->kind == KIND_ROW) blocks = (batch + k->C - 1) / k->C;
@@ -595,7 +695,9 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
             return fail(PHASTFT_ERR_INVALID_ARG, "N == 1 supports only the in-place unscaled form");
         return PHASTFT_OK;
     }
-    if (pl.num_passes == 1) {
+    const bool use_alt_row = pl.alt_row.k != nullptr && batch >= 4;
+    if (pl.num_passes == 1 || use_alt_row) {
+        const int which = use_alt_row ? ALT_ROW_PASS : 0;
         size_t done = 0;
         const size_t max_chunk = (size_t)1 << 24;
         while (done < batch) {
@@ -608,9 +710,12 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
             prm.in_interleaved = io.in_il; prm.out_interleaved = io.out_il;
             prm.scale = scale;
             if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
-            int32_t st = launch_pass(pl, 0, prm, nb, stream);
+            int32_t st = launch_pass(pl, which, prm, nb, stream);
             if (st) return st;
-            if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[1], stream));
+            if (pass_events && done == 0) {
+                CUDA_TRY(cudaEventRecord(pass_events[1], stream));
+                for (int q = 2; q <= pl.num_passes; ++q) CUDA_TRY(cudaEventRecord(pass_events[q], stream));
+            }
             done += nb;
         }
         return PHASTFT_OK;

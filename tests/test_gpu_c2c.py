@@ -195,7 +195,7 @@ def test_interleaved_matches_planar(dt, cdt, n):
 
 # --- device-resident (torch) path and batches -----------------------------------------------------------
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("n,batch", [(8, 1000), (256, 37), (4096, 9), (1 << 13, 5), (1 << 16, 6), (1 << 21, 2)])
+@pytest.mark.parametrize("n,batch", [(8, 1000), (256, 37), (2048, 3), (2048, 11), (4096, 9), (1 << 13, 5), (1 << 16, 6), (1 << 21, 2)])
 def test_device_batch_matches_host_single(dt, n, batch):
     import torch
     pf, O = _pf(), _O()
@@ -211,7 +211,11 @@ def test_device_batch_matches_host_single(dt, n, batch):
         s = slice(b * stride, b * stride + n)
         a, c = re_h[s].copy(), im_h[s].copy()
         fft_with_planner(dt)(a, c, pf.Direction.Forward, planner)
-        assert np.array_equal(g_re[s], a) and np.array_equal(g_im[s], c), (n, b)   # deterministic kernels: bit exact
+        if 10 < n.bit_length() - 1 <= 12:
+            # 2^11..2^12: a lone transform runs as two passes, a batch in the one-CTA kernel (other radix split)
+            assert rel_linf(g_re[s], g_im[s], a, c) <= tol(dt, n), (n, b)
+        else:
+            assert np.array_equal(g_re[s], a) and np.array_equal(g_im[s], c), (n, b)   # deterministic kernels: bit exact
         if stride > n:                               # padding between transforms untouched
             pad = slice(b * stride + n, (b + 1) * stride)
             assert np.array_equal(g_re[pad], re_h[pad])
