@@ -54,7 +54,8 @@ PHASTFT_API void phastft_options_guess(size_t input_size, phastft_options* out);
 
 /* ---- planner.rs:25-32 PlannerMode ------------------------------------------------------ */
 #define PHASTFT_MODE_HEURISTIC 0
-#define PHASTFT_MODE_TUNE 1   /* accepted; the reference ignores the mode (planner.rs:65) */
+#define PHASTFT_MODE_TUNE 1   /* times a few pass decompositions / tile widths at plan time and keeps the fastest
+                                 (the reference accepts the mode and ignores it, planner.rs:65) */
 
 /* ---- planner.rs:34-114 : PlannerDit64 / PlannerDit32 -------------------------------------
  * num_points must be a non-zero power of two (planner.rs:66) else PHASTFT_ERR_NOT_POW2.

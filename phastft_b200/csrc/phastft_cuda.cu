@@ -132,6 +132,8 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
     constexpr bool F64 = sizeof(T) == 8;
     // ---- defaults -------------------------------------------------------------------------------------
+    v.push_back(make_entry_v<T, KIND, 8 * CN, 64, 0, 0, 0, 16>());          // single-stage R=16 (middle pass of e.g. {8,4,8})
+    v.push_back(make_entry_v<T, KIND, 8 * CN, 64, 0, 0, 0, 8>());
     v.push_back(make_entry_v<T, KIND, CH, 32, 0, 0, 0, 8, 8>());
     v.push_back(make_entry_v<T, KIND, CH, 64, 0, 0, 0, 16, 8>());
     v.push_back(make_entry_v<T, KIND, CH, F64 ? 64 : 128, 0, 0, 0, 16, 16>());
@@ -311,9 +313,18 @@ struct Plan {
     }
 };
 
+// An explicit plan choice (PlannerMode::Tune tries several and keeps the fastest); consulted by
+// choose_factors / pick_kernel before the heuristics, like the PHASTFT_FACTORS / PHASTFT_PASS_C env overrides.
+struct PlanChoice {
+    std::vector<int> factors;   // log2 of each pass size
+    std::vector<int> pass_c;    // tile columns per pass (0 = heuristic)
+};
+thread_local const PlanChoice* g_choice = nullptr;
+
 // pass sizes (log2) for a transform of 2^n points -------------------------------------------------
 template <typename T>
 std::vector<int> choose_factors(int n) {
+    if (g_choice && !g_choice->factors.empty()) return g_choice->factors;
     // override: PHASTFT_FACTORS="20:10,10;26:9,9,8"  (applies to both precisions; tuning aid)
     if (const char* env = getenv("PHASTFT_FACTORS")) {
         std::string s(env);
@@ -378,6 +389,8 @@ const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bo
     if (const char* env = getenv("PHASTFT_TILE_C")) want_c = atoi(env);
     if (const char* env = getenv("PHASTFT_VARIANT")) want_variant = atoi(env);
     nth("PHASTFT_PASS_C", want_c);                 // e.g. "16,8,16"
+    if (g_choice && pass_index >= 0 && pass_index < (int)g_choice->pass_c.size() && g_choice->pass_c[pass_index] > 0)
+        want_c = g_choice->pass_c[pass_index];
     nth("PHASTFT_PASS_VARIANT", want_variant);     // e.g. "0,5,0"
     const int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
     const size_t tile_limit = 72 * 1024;           // keep >= 3 CTAs/SM worth of shared memory
@@ -990,6 +1003,78 @@ int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, s
     return PHASTFT_OK;
 }
 
+// ---- PlannerMode::Tune (planner.rs:25-32: "benchmarks both paths at plan time, picks whichever is faster";
+// the reference accepts the mode and ignores it, planner.rs:65).  Here it is real: a handful of pass
+// decompositions / tile widths around the heuristic choice are built, timed on a scratch signal with CUDA
+// events, and the fastest is kept.
+template <typename T>
+int32_t build_plan_tuned(size_t n, int device, Plan<T>** out) {
+    if (!out) return fail(PHASTFT_ERR_INVALID_ARG, "out == NULL");
+    *out = nullptr;
+    int32_t st = build_plan<T>(n, device, out);             // the heuristic plan (also validates n / device)
+    if (st) return st;
+    Plan<T>* best = *out;
+    const int ln = best->log2n;
+    if (best->num_passes < 2) return PHASTFT_OK;            // one-CTA sizes: nothing to choose
+    DeviceGuard guard(device);
+    const int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
+    std::vector<PlanChoice> cands;
+    auto add = [&](std::vector<int> f, std::vector<int> c) { PlanChoice pc; pc.factors = std::move(f); pc.pass_c = std::move(c); cands.push_back(std::move(pc)); };
+    if (ln <= 20) {
+        for (int a : {ln / 2, (ln + 1) / 2})
+            for (int c : {CH, CN, CW}) {
+                if (a > 10 || ln - a > 10 || a < 5 || ln - a < 5) continue;
+                add({a, ln - a}, {c, c});
+            }
+        if (ln >= 18) { add({6, ln - 12, 6}, {CN, CN, CN}); add({7, ln - 14, 7}, {CN, CN, CN}); }
+    } else {
+        for (int e : {7, 8, 9}) {
+            const int m = ln - 2 * e;
+            if (m < 5 || m > 10) continue;
+            add({e, m, e}, {CW, CN, CW});
+            add({e, m, e}, {CN, CN, CN});
+        }
+        if (ln - 18 >= 5 && ln - 18 <= 10) { add({10, ln - 18, 8}, {CN, CN, CW}); add({8, ln - 18, 10}, {CW, CN, CN}); }
+    }
+    T *re = nullptr, *im = nullptr;
+    if (cudaMalloc(&re, n * sizeof(T)) != cudaSuccess || cudaMalloc(&im, n * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        if (re) cudaFree(re);
+        return PHASTFT_OK;                                   // no room to tune: keep the heuristic plan
+    }
+    cudaMemset(re, 0, n * sizeof(T)); cudaMemset(im, 0, n * sizeof(T));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto time_plan = [&](Plan<T>* pl) -> float {
+        const int reps = ln <= 20 ? 20 : (ln <= 24 ? 5 : 2);
+        for (int w = 0; w < 2; ++w) if (fft_dev(pl, re, im, PHASTFT_FORWARD, 1, n, pl->stream) != PHASTFT_OK) return 1e30f;
+        cudaEventRecord(e0, pl->stream);
+        for (int r = 0; r < reps; ++r) fft_dev(pl, re, im, PHASTFT_FORWARD, 1, n, pl->stream);
+        cudaEventRecord(e1, pl->stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) return 1e30f;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        return ms / reps;
+    };
+    float best_ms = time_plan(best);
+    for (const PlanChoice& pc : cands) {
+        Plan<T>* cand = nullptr;
+        g_choice = &pc;
+        int32_t cst = build_plan<T>(n, device, &cand);
+        g_choice = nullptr;
+        if (cst != PHASTFT_OK || !cand) { delete cand; continue; }
+        if (cand->description == best->description) { delete cand; continue; }
+        const float ms = time_plan(cand);
+        if (ms < best_ms * 0.98f) { delete best; best = cand; best_ms = ms; } else delete cand;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(re); cudaFree(im);
+    best->description += " [tuned]";
+    g_last_error.clear();
+    *out = best;
+    return PHASTFT_OK;
+}
+
 // ---- table blob export / import / broadcast ------------------------------------------------------------
 template <typename T>
 int32_t tables_export(const Plan<T>* pl, void* dst, cudaStream_t s) {
@@ -1230,9 +1315,8 @@ void phastft_options_guess(size_t input_size, phastft_options* out) {
 
 #define DEFINE_DIT_API(T, SFX)                                                                                          \
     int32_t phastft_plan_dit_##SFX##_create(size_t n, int device, int mode, phastft_plan_dit_##SFX** out) {             \
-        (void)mode; /* planner.rs:65: the reference ignores the mode as well */                                         \
         Plan<T>* pl = nullptr;                                                                                          \
-        int32_t st = build_plan<T>(n, device, &pl);                                                                     \
+        int32_t st = (mode == PHASTFT_MODE_TUNE) ? build_plan_tuned<T>(n, device, &pl) : build_plan<T>(n, device, &pl); \
         if (out) *out = reinterpret_cast<phastft_plan_dit_##SFX*>(pl);                                                  \
         else if (pl) delete pl;                                                                                         \
         return st;                                                                                                      \

@@ -312,3 +312,34 @@ def test_config_batch_f32_2pow16_linearity_and_oracle():
         o_re, o_im = a[0][s].copy(), a[1][s].copy()
         O.fft_dit(o_re, o_im, O.FORWARD)
         assert rel_linf(A[0][s], A[1][s], o_re, o_im) <= tol(np.float32, n)
+
+
+# --- PlannerMode::Tune is real here: it must stay correct and never be slower than the heuristic plan ----
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("log_n", [14, 18, 22])
+def test_tune_mode_correct_and_not_slower(dt, log_n):
+    import torch
+    pf, O = _pf(), _O()
+    n = 1 << log_n
+    P = pf.PlannerDit64 if dt == np.float64 else pf.PlannerDit32
+    tuned = P.with_mode(n, pf.PlannerMode.Tune)
+    plain = P(n)
+    assert tuned.describe().endswith("[tuned]")
+    re0, im0 = O.gen_random_signal(n, dt, seed=log_n)
+    g_re, g_im = re0.copy(), im0.copy()
+    fft_with_planner(dt)(g_re, g_im, pf.Direction.Forward, tuned)
+    o_re, o_im = re0.copy(), im0.copy()
+    O.fft_dit(o_re, o_im, O.FORWARD)
+    assert rel_linf(g_re, g_im, o_re, o_im) <= tol(dt, n)
+
+    def time_it(pl):
+        d_re = torch.from_numpy(re0).cuda(); d_im = torch.from_numpy(im0).cuda()
+        for _ in range(3):
+            fft_with_planner(dt)(d_re, d_im, pf.Direction.Forward, pl)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            fft_with_planner(dt)(d_re, d_im, pf.Direction.Forward, pl)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    assert time_it(tuned) <= 1.15 * time_it(plain)

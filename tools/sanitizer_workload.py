@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""Workload for `compute-sanitizer --tool memcheck|racecheck python tools/sanitizer_workload.py`:
+every kernel kind, both precisions, lone transforms and batches, r2c/c2r, checked against numpy."""
+import sys
+from pathlib import Path
+import numpy as np
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import phastft_b200 as pf
+import torch
+rng = np.random.default_rng(0)
+for dt, P, f in ((np.float64, pf.PlannerDit64, pf.fft_64_dit_with_planner), (np.float32, pf.PlannerDit32, pf.fft_32_dit_with_planner)):
+    for n in (1, 2, 8, 64, 256, 1024, 4096, 1 << 13, 1 << 15, 1 << 16, 1 << 18, 1 << 21):
+        re = rng.uniform(-1, 1, n).astype(dt); im = rng.uniform(-1, 1, n).astype(dt)
+        pl = P(n)
+        ref = np.fft.fft(re.astype(np.float64) + 1j * im)
+        f(re, im, pf.Direction.Forward, pl)
+        err = np.max(np.abs(re + 1j * im - ref)) / max(np.max(np.abs(ref)), 1e-30)
+        assert err < (1e-13 if dt == np.float64 else 1e-5), (dt, n, err)
+    for n, b in ((256, 40), (2048, 9), (4096, 5), (1 << 16, 40)):
+        pl = P(n)
+        tdt = torch.float64 if dt == np.float64 else torch.float32
+        d_re = torch.rand(n * b, dtype=tdt, device="cuda"); d_im = torch.rand(n * b, dtype=tdt, device="cuda")
+        x = (d_re.cpu().numpy().astype(np.float64) + 1j * d_im.cpu().numpy()).reshape(b, n)
+        pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, pl, b)
+        got = (d_re.cpu().numpy().astype(np.float64) + 1j * d_im.cpu().numpy()).reshape(b, n)
+        ref = np.fft.fft(x, axis=1)
+        assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < (1e-13 if dt == np.float64 else 1e-5), (dt, n, b)
+for n in (4, 64, 4096, 1 << 15):
+    x = rng.uniform(-1, 1, n)
+    ore = np.zeros(n // 2 + 1); oim = np.zeros(n // 2 + 1)
+    pf.r2c_fft_f64(x, ore, oim)
+    assert np.max(np.abs(ore + 1j * oim - np.fft.rfft(x))) < 1e-10
+    y = np.zeros(n); pf.c2r_fft_f64(ore, oim, y)
+    assert np.max(np.abs(y - x)) < 1e-12
+print("sanitizer workload ok")
