@@ -220,7 +220,8 @@ def run_reference(args):
 
 
 def planner_passes(planner) -> int:
-    return planner.describe().split(" || ")[0].count(" | ") + 1
+    d = planner.describe().split(" || ")[0]
+    return 1 if "[fused launch" in d else d.count(" | ") + 1
 
 
 def workload_config(workload: str, gpus: int):

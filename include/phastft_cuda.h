@@ -73,6 +73,11 @@ PHASTFT_API size_t phastft_plan_dit_f32_size(const phastft_plan_dit_f32* plan);
 PHASTFT_API const char* phastft_plan_dit_f64_describe(const phastft_plan_dit_f64* plan);
 PHASTFT_API const char* phastft_plan_dit_f32_describe(const phastft_plan_dit_f32* plan);
 
+/* Host-only planning logic (no device needed): the pass decomposition N = 2^f0 * 2^f1 [* 2^f2] the
+ * planner uses for `num_points` (one CTA per transform when *num_passes == 1; 0 passes for N == 1).
+ * log2_factors must hold 3 ints. */
+PHASTFT_API int32_t phastft_plan_factorization(size_t num_points, int precision_bits, int* log2_factors, int* num_passes);
+
 /* Planner-table blob (multi-GPU init): rank 0 exports its tables into a
  * device buffer, the host framework broadcasts that buffer once (ncclBroadcast /
  * torch.distributed.broadcast), every other rank imports it.  No per-call collectives. */

@@ -98,7 +98,24 @@ SIGNATURES = {
     "phastft_c2r_{s}_oneshot": ([_vp, _sz, _vp, _sz, _vp, _sz, _ci], _i32),
     "phastft_c2r_{s}_dev": ([_vp, _vp, _vp, _vp, _vp, _vp, _vp], _i32),
 }
-GLOBAL_SYMBOLS = ["phastft_last_error", "phastft_version", "phastft_launch_count", "phastft_device_count",
+def check(code: int):
+    if code != OK:
+        raise PhastFTPanic(code, (lib.phastft_last_error() or b"").decode())
+
+
+lib.phastft_plan_factorization.argtypes = [_sz, _ci, C.POINTER(_ci), C.POINTER(_ci)]
+lib.phastft_plan_factorization.restype = _i32
+
+
+def plan_factorization(n: int, precision_bits: int = 64):
+    """Host-only: log2 of the pass sizes the planner uses for an n-point transform."""
+    f = (_ci * 3)()
+    k = _ci(0)
+    check(lib.phastft_plan_factorization(int(n), int(precision_bits), f, C.byref(k)))
+    return [f[i] for i in range(k.value)]
+
+
+GLOBAL_SYMBOLS = ["phastft_plan_factorization", "phastft_last_error", "phastft_version", "phastft_launch_count", "phastft_device_count",
                   "phastft_options_default", "phastft_options_guess"]
 
 for _name, (_args, _res) in SIGNATURES.items():
@@ -112,9 +129,6 @@ def fn(name: str, sfx: str):
     return getattr(lib, name.format(s=sfx))
 
 
-def check(code: int):
-    if code != OK:
-        raise PhastFTPanic(code, (lib.phastft_last_error() or b"").decode())
 
 
 def launch_count() -> int:

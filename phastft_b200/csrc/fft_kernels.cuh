@@ -143,7 +143,7 @@ struct PassKernel {
     // ---- one register-resident stage s >= 1 (0-based), reading from the tile ------------------
     template <int s>
     static __device__ __forceinline__ void stage_from_tile(const PassParams<T>& p, cx<T>* tile, long long out_base,
-                                                           long long out_kstride, int tile_rows_valid) {
+                                                           long long out_kstride, int tile_rows_valid, int tid) {
         constexpr int RAD = RL::rad(s);
         constexpr int NS = RL::Ns(s);
         constexpr int J = R / RAD;                      // tasks per column
@@ -152,7 +152,7 @@ struct PassKernel {
         constexpr int NTASK = J * C;
         constexpr int TRIPS = (NTASK + NT - 1) / NT;
 #pragma unroll((VARIANT & 1) ? TRIPS : 1)
-        for (int t = threadIdx.x; t < NTASK; t += NT) {
+        for (int t = tid; t < NTASK; t += NT) {
             int c, j;
             if constexpr (KIND == KIND_ROW) { j = t % J; c = t / J; } else { c = t % C; j = t / C; }
             const int m = j & (NS - 1);
@@ -207,22 +207,25 @@ struct PassKernel {
 
     template <int s>
     static __device__ __forceinline__ void run_stages(const PassParams<T>& p, cx<T>* tile, long long out_base,
-                                                      long long out_kstride, int rows_valid) {
+                                                      long long out_kstride, int rows_valid, int tid) {
         if constexpr (s < S) {
             __syncthreads();
-            stage_from_tile<s>(p, tile, out_base, out_kstride, rows_valid);
-            run_stages<s + 1>(p, tile, out_base, out_kstride, rows_valid);
+            stage_from_tile<s>(p, tile, out_base, out_kstride, rows_valid, tid);
+            run_stages<s + 1>(p, tile, out_base, out_kstride, rows_valid, tid);
         }
     }
 
     // ---- the kernel body ------------------------------------------------------------------------
-    static __device__ __forceinline__ void body(const PassParams<T>& p) {
+    // `tile_index` is the linear tile id (blockIdx.x for a plain launch; a fused launch loops over tiles).
+    // Threads with threadIdx.x >= NT (a fused launch whose other pass needs more threads) take part in
+    // the barriers only: their task index starts beyond every task count.
+    static __device__ __forceinline__ void body(const PassParams<T>& p, unsigned tile_index) {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         cx<T>* tile = reinterpret_cast<cx<T>*>(smem_raw);
         cx<T>* s_um = tile + TILE_ELEMS;   // [M]       per-CTA  W_L^(kp*B*m')
         cx<T>* s_g = s_um + M;             // [C][R1] or [R1]     W_L^(kp(c)*M*B*i)
 
-        const int tid = threadIdx.x;
+        const int tid = (threadIdx.x < NT) ? (int)threadIdx.x : (1 << 28);
         // Programmatic dependent launch (sm_90+): this grid may have been scheduled while the previous
         // pass is still draining; wait for its memory to be visible before touching global data, and
         // let the next pass's CTAs be scheduled as soon as every CTA of this grid is resident.
@@ -240,7 +243,7 @@ struct PassKernel {
 
         if constexpr (KIND == KIND_COL) {
             const int tilesB = 1 << (p.log2B - LOG2C);
-            const unsigned blk = blockIdx.x + (unsigned)p.blk_offset;
+            const unsigned blk = tile_index + (unsigned)p.blk_offset;
             const int bt = blk & (tilesB - 1);
             const int rest = blk >> (p.log2B - LOG2C);
             const int a = rest & ((1 << p.log2A) - 1);
@@ -257,8 +260,8 @@ struct PassKernel {
             // rows of the tile: a(c) = (k0 + c) * rest_n + rest, rest_n = A / R1
             const int log2restn = p.log2A - p.log2R1;
             const int tilesK = 1 << p.log2_ktn;
-            const int kt = p.kt_base + (blockIdx.x & (tilesK - 1));
-            const int tmp = blockIdx.x >> p.log2_ktn;
+            const int kt = p.kt_base + (tile_index & (tilesK - 1));
+            const int tmp = tile_index >> p.log2_ktn;
             const int rest = tmp & ((1 << log2restn) - 1);
             const int batch = tmp >> log2restn;
             const int k0 = kt << LOG2C;
@@ -272,7 +275,7 @@ struct PassKernel {
             kp0 = (uint32_t)(((long long)k0 << log2restn) + rest) & rprev_mask;
             kp_cstep = (log2restn == 0) ? 1u : 0u;   // 2-pass plan: kp = k1 = k0 + c ; 3-pass: kp = k2
         } else {
-            const long long first = (long long)blockIdx.x * C;
+            const long long first = (long long)tile_index * C;
             rows_valid = (int)min((long long)C, (long long)p.batch - first);
             in_base = first * p.in_bstride;
             out_base = first * p.out_bstride;
@@ -427,13 +430,54 @@ struct PassKernel {
             }
         }
         // ---- stages 2..S -------------------------------------------------------------------------
-        run_stages<1>(p, tile, out_base, out_kstride, rows_valid);
+        run_stages<1>(p, tile, out_base, out_kstride, rows_valid, tid);
     }
 };
 
 template <typename T, class RL, int C, int NT, int KIND, int ASYNC, int VARIANT = 0, int MINB = 0>
 __global__ void __launch_bounds__(NT, MINB) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {
-    PassKernel<T, RL, C, NT, KIND, ASYNC, VARIANT>::body(p);
+    PassKernel<T, RL, C, NT, KIND, ASYNC, VARIANT>::body(p, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused two-pass launch for signals that live in L2 (N <= 2^20): ONE cooperative grid runs the tiles
+// of pass 1, meets at a grid-wide barrier, then runs the tiles of pass 2.  At these sizes a pass is a
+// single latency-bound wave and a launch costs ~2.5 us of a ~10 us pass, so removing one launch (and
+// the drain/fill between the passes) is worth 10-30 %.
+// bar[0] = arrival count, bar[1] = generation; self-resetting, so CUDA-graph replays can reuse it.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        volatile unsigned* vgen = bar + 1;
+        const unsigned gen = *vgen;
+        const unsigned prev = atomicAdd(bar, 1u);
+        if (prev == nblocks - 1) {
+            bar[0] = 0;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*vgen == gen) __nanosleep(32);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <class PK1, class PK2, typename T, int NTF, int MINB>
+__global__ void __launch_bounds__(NTF, MINB) fft_fused2_kernel(const __grid_constant__ PassParams<T> p1,
+                                                              const __grid_constant__ PassParams<T> p2,
+                                                              unsigned tiles1, unsigned tiles2, unsigned* bar) {
+    for (unsigned t = blockIdx.x; t < tiles1; t += gridDim.x) {
+        PK1::body(p1, t);
+        __syncthreads();
+    }
+    grid_barrier(bar, gridDim.x);
+    for (unsigned t = blockIdx.x; t < tiles2; t += gridDim.x) {
+        PK2::body(p2, t);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -109,12 +109,6 @@ KernelEntry<T> make_entry_a() {
 }
 template <typename T, int KIND, int C, int NT, int... Rs>
 KernelEntry<T> make_entry() { return make_entry_a<T, KIND, C, NT, 0, Rs...>(); }
-// register both the register-staged and the cp.async variant of a strided-kind kernel
-template <typename T, int KIND, int C, int NT, int... Rs>
-void add_both(std::vector<KernelEntry<T>>& v) {
-    v.push_back(make_entry_a<T, KIND, C, NT, 0, Rs...>());
-    v.push_back(make_entry_a<T, KIND, C, NT, 1, Rs...>());
-}
 
 // Tile width in columns for the strided (HBM-facing) kinds: C * sizeof(T) = 64 B (CN) or 128 B (CW).
 template <typename T> struct TileC;
@@ -213,6 +207,68 @@ const std::vector<KernelEntry<T>>& registry() {
     return reg;
 }
 
+// ---- fused two-pass launches (fft_fused2_kernel) for the default 2-pass plans of lone transforms ----------
+template <typename T>
+struct FusedEntry {
+    int R1, C1, NT1, R2, C2, NT2;
+    std::string rad1, rad2;
+    const void* fn;
+    int NT;
+    size_t smem;
+};
+template <class RL> std::string radix_string() {
+    std::string r;
+    for (int i = 0; i < RL::S; ++i) r += (i ? "x" : "") + std::to_string(RL::rad(i));
+    return r;
+}
+template <typename T, class RL1, int C1, int NT1, int V1, class RL2, int C2, int NT2, int V2>
+FusedEntry<T> make_fused() {
+    using PK1 = PassKernel<T, RL1, C1, NT1, KIND_COL, 0, V1>;
+    using PK2 = PassKernel<T, RL2, C2, NT2, KIND_TRANS, 0, V2>;
+    constexpr int NTF = NT1 > NT2 ? NT1 : NT2;
+    FusedEntry<T> e;
+    e.R1 = RL1::R(); e.C1 = C1; e.NT1 = NT1; e.R2 = RL2::R(); e.C2 = C2; e.NT2 = NT2;
+    e.rad1 = radix_string<RL1>(); e.rad2 = radix_string<RL2>();
+    e.fn = reinterpret_cast<const void*>(&fft_fused2_kernel<PK1, PK2, T, NTF, 1>);
+    e.NT = NTF;
+    e.smem = PK1::SMEM_BYTES > PK2::SMEM_BYTES ? PK1::SMEM_BYTES : PK2::SMEM_BYTES;
+    return e;
+}
+// The pairs are exactly the default 2-pass plans 2^11..2^20 (tools/tune17.py prints them); the knob
+// values (V) repeat the ones of the default registry entries so fused and unfused results are bit-identical.
+template <typename T>
+const std::vector<FusedEntry<T>>& fused_registry() {
+    static const std::vector<FusedEntry<T>> reg = [] {
+        std::vector<FusedEntry<T>> v;
+        constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN;
+        using R32 = RadixList<4, 8>; using R64 = RadixList<8, 8>; using R128 = RadixList<16, 8>;
+        using R256 = RadixList<16, 16>; using R512 = RadixList<8, 8, 8>; using R1024 = RadixList<16, 8, 8>;
+        if constexpr (sizeof(T) == 8) {
+            v.push_back(make_fused<T, R32, CN, 32, 0, R64, CH, 32, 0>());          // 2^11
+            v.push_back(make_fused<T, R64, CH, 32, 0, R64, CH, 32, 0>());          // 2^12
+            v.push_back(make_fused<T, R64, CH, 32, 0, R128, CH, 64, 0>());         // 2^13
+            v.push_back(make_fused<T, R128, CH, 64, 0, R128, CH, 64, 0>());        // 2^14
+            v.push_back(make_fused<T, R128, CH, 64, 0, R256, CH, 64, 0>());        // 2^15
+            v.push_back(make_fused<T, R256, CH, 64, 0, R256, CH, 64, 0>());        // 2^16
+            v.push_back(make_fused<T, R512, CH, 256, 3, R256, CH, 64, 0>());       // 2^17
+            v.push_back(make_fused<T, R512, CH, 256, 3, R512, CH, 256, 3>());      // 2^18
+            v.push_back(make_fused<T, R1024, CH, 512, 0, R512, CH, 256, 3>());     // 2^19
+            v.push_back(make_fused<T, R1024, CN, 512, 0, R1024, CN, 512, 0>());    // 2^20
+        } else {
+            v.push_back(make_fused<T, R64, CH, 32, 0, R128, CH, 64, 0>());         // 2^13
+            v.push_back(make_fused<T, R128, CH, 64, 0, R128, CH, 64, 0>());        // 2^14
+            v.push_back(make_fused<T, R128, CH, 64, 0, R256, CH, 128, 0>());       // 2^15
+            v.push_back(make_fused<T, R256, CH, 128, 0, R256, CH, 128, 0>());      // 2^16
+            v.push_back(make_fused<T, R512, CH, 256, 3, R256, CH, 128, 0>());      // 2^17
+            v.push_back(make_fused<T, R512, CH, 256, 3, R512, CH, 256, 3>());      // 2^18
+            v.push_back(make_fused<T, R1024, CH, 256, 0, R512, CH, 256, 3>());     // 2^19
+            v.push_back(make_fused<T, R1024, CH, 256, 0, R1024, CH, 256, 0>());    // 2^20
+        }
+        return v;
+    }();
+    return reg;
+}
+
 const char* kind_name(int k) { return k == KIND_COL ? "COL" : k == KIND_TRANS ? "TRANS" : "ROW"; }
 
 // =================================================================================================
@@ -277,6 +333,9 @@ struct Plan {
     int num_passes = 0;
     PassDesc<T> pass[MAX_PASSES];
     PassDesc<T> alt_row;               // N <= 4096 planned as two passes: the one-CTA kernel, used for batches
+    const FusedEntry<T>* fused = nullptr;   // 2-pass plans: both passes in one cooperative launch (lone transforms)
+    int fused_grid = 0;
+    unsigned* fuse_bar = nullptr;      // grid barrier state {count, generation}
     // table blob: [tw2_hi][tw2_lo][per pass W_R][wc]
     std::vector<unsigned char> blob_host;
     unsigned char* blob_dev = nullptr;
@@ -304,6 +363,7 @@ struct Plan {
         if (blob_dev) cudaFree(blob_dev);
         if (ws_re) cudaFree(ws_re);
         if (ws_im) cudaFree(ws_im);
+        if (fuse_bar) cudaFree(fuse_bar);
         if (ws2_re) cudaFree(ws2_re);
         if (ws2_im) cudaFree(ws2_im);
         if (stage_re) cudaFree(stage_re);
@@ -588,6 +648,30 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             CUDA_TRY(cudaMalloc(&pl->ws2_im, (size_t)G * (n >> f[0]) * sizeof(T)));
         }
     }
+    if (pl->num_passes == 2) {
+        // measured slower than two plain launches (tools/tune21.py: 2^20 f64 23.6 vs 21.1 us, 2^16 8.8 vs 7.8 us):
+        // the cooperative launch and the grid barrier cost more than the launch they save.  Off by default.
+        static const bool use_fuse = [] { const char* e = getenv("PHASTFT_FUSE"); return e ? atoi(e) != 0 : false; }();
+        const KernelEntry<T>* a = pl->pass[0].k; const KernelEntry<T>* b = pl->pass[1].k;
+        if (use_fuse)
+            for (const auto& fe : fused_registry<T>())
+                if (fe.R1 == a->R && fe.C1 == a->C && fe.NT1 == a->NT && fe.rad1 == a->radices && fe.R2 == b->R && fe.C2 == b->C &&
+                    fe.NT2 == b->NT && fe.rad2 == b->radices) { pl->fused = &fe; break; }
+        if (pl->fused) {
+            int occ = 0, sms = 0, coop = 0;
+            CUDA_TRY(cudaFuncSetAttribute(pl->fused->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fused->smem));
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+            CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pl->fused->fn, pl->fused->NT, pl->fused->smem));
+            const size_t tiles = std::max((n >> f[0]) / a->C, (n >> f[1]) / b->C);
+            pl->fused_grid = (int)std::min<size_t>(tiles, (size_t)sms * std::max(occ, 0));
+            if (!coop || occ < 1 || pl->fused_grid < 1) pl->fused = nullptr;
+            else {
+                CUDA_TRY(cudaMalloc(&pl->fuse_bar, 2 * sizeof(unsigned)));
+                CUDA_TRY(cudaMemset(pl->fuse_bar, 0, 2 * sizeof(unsigned)));
+            }
+        }
+    }
     // description
     {
         std::string s = "n=2^" + std::to_string(ln) + (sizeof(T) == 8 ? " f64:" : " f32:");
@@ -608,6 +692,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                      std::to_string(k->C) + " NT=" + std::to_string(k->NT);
             }
         }
+        if (pl->fused) s += " [fused launch, grid " + std::to_string(pl->fused_grid) + "]";
         if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
         pl->description = s;
     }
@@ -629,8 +714,41 @@ struct Io {
 // k1_lo / k1_cnt (multi-pass plans, batch == 1): restrict a pass AFTER the first to the sub-transforms
 // whose first-pass output digit k1 lies in [k1_lo, k1_lo + k1_cnt) -- the unit of L2 blocking.
 template <typename T>
+int32_t prepare_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, long long k1_lo, long long k1_cnt,
+                     PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out);
+
+template <typename T>
 int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, cudaStream_t stream,
                     long long k1_lo = 0, long long k1_cnt = -1) {
+    PassParams<T> prm;
+    const KernelEntry<T>* k = nullptr;
+    unsigned long long blocks = 0;
+    int32_t st = prepare_pass(pl, p, base, batch, k1_lo, k1_cnt, prm, k, blocks);
+    if (st) return st;
+    void* args[] = {&prm};
+    static const bool use_pdl = [] { const char* e = getenv("PHASTFT_PDL"); return e ? atoi(e) != 0 : false; }();   // measured: no gain at 2^20, -10% at 2^24+ (tune8)
+    if (use_pdl) {
+        // Programmatic dependent launch: back-to-back passes overlap the next grid's launch and prologue
+        // with the previous grid's tail (the kernel waits with griddepcontrol.wait before its first access).
+        prm.pdl = 1;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(k->NT); cfg.dynamicSmemBytes = k->smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, k->fn, args));
+    } else {
+        CUDA_TRY(cudaLaunchKernel(k->fn, dim3((unsigned)blocks), dim3(k->NT), args, k->smem, stream));
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t prepare_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, long long k1_lo, long long k1_cnt,
+                     PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out) {
     const PassDesc<T>& d = (p == ALT_ROW_PASS) ? pl.alt_row : pl.pass[p];
     const bool many = d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
     const KernelEntry<T>* k = many ? d.kb : d.k;
@@ -660,24 +778,7 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
         }
     }
     if (blocks == 0 || blocks > 0x7fffffffULL) return fail(PHASTFT_ERR_INVALID_ARG, "grid too large");
-    void* args[] = {&prm};
-    static const bool use_pdl = [] { const char* e = getenv("PHASTFT_PDL"); return e ? atoi(e) != 0 : false; }();   // measured: no gain at 2^20, -10% at 2^24+ (tune8)
-    if (use_pdl) {
-        // Programmatic dependent launch: back-to-back passes overlap the next grid's launch and prologue
-        // with the previous grid's tail (the kernel waits with griddepcontrol.wait before its first access).
-        prm.pdl = 1;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(k->NT); cfg.dynamicSmemBytes = k->smem; cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelExC(&cfg, k->fn, args));
-    } else {
-        CUDA_TRY(cudaLaunchKernel(k->fn, dim3((unsigned)blocks), dim3(k->NT), args, k->smem, stream));
-    }
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    prm_out = prm; k_out = k; blocks_out = blocks;
     return PHASTFT_OK;
 }
 
@@ -758,6 +859,36 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     const bool capturing = cap != cudaStreamCaptureStatusNone;
     if (!capturing && pl.ws_last_stream != stream && pl.ws_used) CUDA_TRY(cudaStreamWaitEvent(stream, pl.ws_free, 0));
     const int P = pl.num_passes;
+    if (P == 2 && pl.fused && batch == 1 && !pass_events) {
+        PassParams<T> b1, b2, p1, p2;
+        memset(&b1, 0, sizeof(b1)); memset(&b2, 0, sizeof(b2));
+        b1.scale = T(1);
+        b1.in_re = io.in_re; b1.in_im = io.in_im; b1.in_bstride = io.in_bstride; b1.in_interleaved = io.in_il;
+        b1.out_re = pl.ws_re; b1.out_im = pl.ws_im; b1.out_bstride = (long long)pl.n;
+        b2.in_re = pl.ws_re; b2.in_im = pl.ws_im; b2.in_bstride = (long long)pl.n;
+        b2.out_re = io.out_re; b2.out_im = io.out_im; b2.out_bstride = io.out_bstride; b2.out_interleaved = io.out_il;
+        b2.scale = scale;
+        const KernelEntry<T>* k1 = nullptr; const KernelEntry<T>* k2 = nullptr;
+        unsigned long long t1 = 0, t2 = 0;
+        int32_t st = prepare_pass(pl, 0, b1, 1, 0, -1, p1, k1, t1);
+        if (!st) st = prepare_pass(pl, 1, b2, 1, 0, -1, p2, k2, t2);
+        if (st) return st;
+        unsigned tiles1 = (unsigned)t1, tiles2 = (unsigned)t2;
+        unsigned* bar = pl.fuse_bar;
+        void* args[] = {&p1, &p2, &tiles1, &tiles2, &bar};
+        static const int fuse_mode = [] { const char* e = getenv("PHASTFT_FUSE"); return e ? atoi(e) : 0; }();
+        if (fuse_mode == 2)   // plain launch: the grid is sized to be co-resident, so the barrier cannot deadlock in practice
+            CUDA_TRY(cudaLaunchKernel(pl.fused->fn, dim3((unsigned)pl.fused_grid), dim3(pl.fused->NT), args, pl.fused->smem, stream));
+        else
+            CUDA_TRY(cudaLaunchCooperativeKernel(pl.fused->fn, dim3((unsigned)pl.fused_grid), dim3(pl.fused->NT), args, pl.fused->smem, stream));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (!capturing) {
+            CUDA_TRY(cudaEventRecord(pl.ws_free, stream));
+            pl.ws_last_stream = stream;
+            pl.ws_used = true;
+        }
+        return PHASTFT_OK;
+    }
     // ---- 3-pass plans: pass 1 streams the whole signal HBM -> HBM; passes 2+3 then run per group of
     // G consecutive k1 values (G * N/R1 elements ~ tens of MiB): pass 2 writes its result into a small
     // reused scratch that stays L2-resident and pass 3 reads it back from L2, so the tail costs one
@@ -1299,6 +1430,17 @@ int32_t phastft_device_count(int* count) {
     *count = 0;
     cudaError_t e = cudaGetDeviceCount(count);
     if (e != cudaSuccess || *count == 0) { *count = 0; return fail(PHASTFT_ERR_NO_DEVICE, e != cudaSuccess ? cudaGetErrorString(e) : ""); }
+    return PHASTFT_OK;
+}
+
+int32_t phastft_plan_factorization(size_t n, int precision_bits, int* log2_factors, int* num_passes) {
+    if (!log2_factors || !num_passes) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
+    if (!is_pow2(n)) return fail(PHASTFT_ERR_NOT_POW2);
+    if (precision_bits != 32 && precision_bits != 64) return fail(PHASTFT_ERR_INVALID_ARG, "precision_bits must be 32 or 64");
+    const int ln = ilog2(n);
+    std::vector<int> f = ln == 0 ? std::vector<int>{} : (precision_bits == 64 ? choose_factors<double>(ln) : choose_factors<float>(ln));
+    *num_passes = (int)f.size();
+    for (size_t i = 0; i < f.size(); ++i) log2_factors[i] = f[i];
     return PHASTFT_OK;
 }
 

@@ -93,3 +93,25 @@ def test_product_never_imports_the_oracle():
         if p.suffix in (".py", ".cu", ".cuh", ".h", ".hpp"):
             assert "oracle" not in p.read_text().lower().replace("the cpu oracle", "").replace("oracle/", "ORACLEDIR") \
                 or p.name == "__init__.py", p
+
+
+def test_planner_factorization_host_logic(pf):
+    """The pass decomposition is pure host logic: N = prod 2^f_i, every pass size has a kernel (2^1..2^10 for
+    the strided kinds, one CTA up to 2^10 f64 / 2^12 f32), at most three passes."""
+    from phastft_b200 import _lib
+    for bits, single_max in ((64, 10), (32, 12)):
+        assert _lib.plan_factorization(1, bits) == []
+        for ln in range(1, 31):
+            f = _lib.plan_factorization(1 << ln, bits)
+            assert sum(f) == ln and 1 <= len(f) <= 3, (ln, f)
+            if ln <= single_max:
+                assert f == [ln]
+            else:
+                assert len(f) >= 2 and all(5 <= x <= 10 for x in f), (ln, f)
+            if len(f) == 3 and ln <= 26:
+                assert f[0] == f[2] and f[0] in (7, 8)          # 128-byte-run end tiles stay at <= 256 rows
+    assert _lib.plan_factorization(1 << 20, 64) == [10, 10]
+    assert _lib.plan_factorization(1 << 26, 64) == [8, 10, 8]
+    assert _lib.plan_factorization(1 << 16, 32) == [8, 8]
+    with pytest.raises(pf.PhastFTPanic):
+        _lib.plan_factorization(12, 64)
