@@ -150,6 +150,42 @@ template <typename T> struct Dft<T, 16> {
     }
 };
 
+// Radix 32: two radix-16 halves + one level of W_32^k butterflies. 64 live scalars per thread: only
+// worth it where it removes a whole shared-memory exchange (1024 = 32*32 in two stages).
+template <typename T> struct Dft<T, 32> {
+    static __device__ __forceinline__ void run(T (&r)[32], T (&i)[32]) {
+        T er[16], ei[16], orr[16], oi[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { er[k] = r[2 * k]; ei[k] = i[2 * k]; orr[k] = r[2 * k + 1]; oi[k] = i[2 * k + 1]; }
+        Dft<T, 16>::run(er, ei);
+        Dft<T, 16>::run(orr, oi);
+        const T c1 = T(0.980785280403230449126182236134239036973934);  // cos(pi/16)
+        const T s1 = T(0.195090322016128267848284868477022240927692);  // sin(pi/16)
+        const T c2 = T(0.923879532511286756128183189396788286822417);  // cos(2pi/16)
+        const T s2 = T(0.382683432365089771728459984030398866761345);  // sin(2pi/16)
+        const T c3 = T(0.831469612302545237078788377617905756738561);  // cos(3pi/16)
+        const T s3 = T(0.555570233019602224742830813948532874374937);  // sin(3pi/16)
+        bf_1(er[0], ei[0], orr[0], oi[0]);
+        bf_w(er[1], ei[1], orr[1], oi[1], c1, -s1);
+        bf_w(er[2], ei[2], orr[2], oi[2], c2, -s2);
+        bf_w(er[3], ei[3], orr[3], oi[3], c3, -s3);
+        bf_w8_1(er[4], ei[4], orr[4], oi[4]);
+        bf_w(er[5], ei[5], orr[5], oi[5], s3, -c3);
+        bf_w(er[6], ei[6], orr[6], oi[6], s2, -c2);
+        bf_w(er[7], ei[7], orr[7], oi[7], s1, -c1);
+        bf_mj(er[8], ei[8], orr[8], oi[8]);
+        bf_w(er[9], ei[9], orr[9], oi[9], -s1, -c1);
+        bf_w(er[10], ei[10], orr[10], oi[10], -s2, -c2);
+        bf_w(er[11], ei[11], orr[11], oi[11], -s3, -c3);
+        bf_w8_3(er[12], ei[12], orr[12], oi[12]);
+        bf_w(er[13], ei[13], orr[13], oi[13], -c3, -s3);
+        bf_w(er[14], ei[14], orr[14], oi[14], -c2, -s2);
+        bf_w(er[15], ei[15], orr[15], oi[15], -c1, -s1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { r[k] = er[k]; i[k] = ei[k]; r[k + 16] = orr[k]; i[k + 16] = oi[k]; }
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // Compile-time radix lists.
 // ---------------------------------------------------------------------------------------------

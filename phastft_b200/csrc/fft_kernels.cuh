@@ -23,6 +23,7 @@
 //              digit-reversing transpose, written as C-element contiguous runs.
 //   KIND_ROW   whole transform in one CTA (N <= 4096 f64 / 8192 f32): rows contiguous in and out.
 #pragma once
+#include <type_traits>
 
 #include "fft_device.cuh"
 
@@ -140,8 +141,58 @@ struct PassKernel {
         }
     }
 
-    // ---- one register-resident stage s >= 1 (0-based), reading from the tile ------------------
-    template <int s>
+    // N strided elements at once.  The layout test is hoisted out of the unrolled loop so each layout gets
+    // its own straight-line block behind a uniform branch: with the test inside the loop the compiler
+    // predicates both layouts into one stream (every launch then issues the other layout's dead loads and
+    // selects, and the selects of the interleaved path split its loads into two dependent batches).
+    // Layout class: 0 planar, 1 interleaved (re, im), 2 interleaved swapped (im, re), -1 = test at run time.
+    template <int N, int IL = -1>
+    static __device__ __forceinline__ void gload_n(const PassParams<T>& p, long long a0, long long step, T (&re)[N], T (&im)[N]) {
+        if constexpr (IL < 0) {
+            if (p.in_interleaved == 0) gload_n<N, 0>(p, a0, step, re, im);
+            else if (p.in_interleaved == 1) gload_n<N, 1>(p, a0, step, re, im);
+            else gload_n<N, 2>(p, a0, step, re, im);
+        } else if constexpr (IL == 0) {
+            const T* pr = p.in_re + a0;
+            const T* pi = p.in_im + a0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) { re[i] = pr[(long long)i * step]; im[i] = pi[(long long)i * step]; }
+        } else {
+            const cx<T>* pc = reinterpret_cast<const cx<T>*>(p.in_re) + a0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const cx<T> v = pc[(long long)i * step];
+                if constexpr (IL == 1) { re[i] = v.x; im[i] = v.y; } else { re[i] = v.y; im[i] = v.x; }
+            }
+        }
+    }
+    template <int N, int OL = -1>
+    static __device__ __forceinline__ void gstore_n(const PassParams<T>& p, long long a0, long long step, T (&re)[N], T (&im)[N]) {
+        if constexpr (OL < 0) {
+            if (p.out_interleaved == 0) gstore_n<N, 0>(p, a0, step, re, im);
+            else if (p.out_interleaved == 1) gstore_n<N, 1>(p, a0, step, re, im);
+            else gstore_n<N, 2>(p, a0, step, re, im);
+        } else {
+            if (p.scale != T(1)) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) { re[i] *= p.scale; im[i] *= p.scale; }
+            }
+            if constexpr (OL == 0) {
+                T* pr = p.out_re + a0;
+                T* pi = p.out_im + a0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) { pr[(long long)i * step] = re[i]; pi[(long long)i * step] = im[i]; }
+            } else {
+                cx<T>* pc = reinterpret_cast<cx<T>*>(p.out_re) + a0;
+#pragma unroll
+                for (int i = 0; i < N; ++i) pc[(long long)i * step] = (OL == 1) ? make_cx<T>(re[i], im[i]) : make_cx<T>(im[i], re[i]);
+            }
+        }
+    }
+
+    // OL: output layout class of the LAST stage's stores (see gload_n); the test is made once
+    // per stage (run_stages), outside the task loop, so each layout is a straight-line loop.
+    template <int s, int OL = -1>
     static __device__ __forceinline__ void stage_from_tile(const PassParams<T>& p, cx<T>* tile, long long out_base,
                                                            long long out_kstride, int tile_rows_valid, int tid) {
         constexpr int RAD = RL::rad(s);
@@ -194,13 +245,8 @@ struct PassKernel {
             } else {
                 // last stage: g == 0, natural-order outputs kr = m + k*NS
                 if (KIND == KIND_ROW && c >= tile_rows_valid) continue;
-#pragma unroll
-                for (int k = 0; k < RAD; ++k) {
-                    long long idx;
-                    if constexpr (KIND == KIND_ROW) idx = out_base + (long long)c * p.out_bstride + (m + k * NS);
-                    else idx = out_base + (long long)(m + k * NS) * out_kstride + c;
-                    gstore(p, idx, xr[k], xi[k]);
-                }
+                if constexpr (KIND == KIND_ROW) gstore_n<RAD, OL>(p, out_base + (long long)c * p.out_bstride + m, (long long)NS, xr, xi);
+                else gstore_n<RAD, OL>(p, out_base + (long long)m * out_kstride + c, (long long)NS * out_kstride, xr, xi);
             }
         }
     }
@@ -210,7 +256,13 @@ struct PassKernel {
                                                       long long out_kstride, int rows_valid, int tid) {
         if constexpr (s < S) {
             __syncthreads();
-            stage_from_tile<s>(p, tile, out_base, out_kstride, rows_valid, tid);
+            if constexpr (s == S - 1) {
+                if (p.out_interleaved == 0) stage_from_tile<s, 0>(p, tile, out_base, out_kstride, rows_valid, tid);
+                else if (p.out_interleaved == 1) stage_from_tile<s, 1>(p, tile, out_base, out_kstride, rows_valid, tid);
+                else stage_from_tile<s, 2>(p, tile, out_base, out_kstride, rows_valid, tid);
+            } else {
+                stage_from_tile<s>(p, tile, out_base, out_kstride, rows_valid, tid);
+            }
             run_stages<s + 1>(p, tile, out_base, out_kstride, rows_valid, tid);
         }
     }
@@ -320,8 +372,7 @@ struct PassKernel {
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
                 if ((KIND != KIND_ROW) || (c < rows_valid)) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
-#pragma unroll
-                    for (int i = 0; i < R1; ++i) gload(p, a0 + (long long)(i * M) * in_rstride, pre_r[i], pre_i[i]);
+                    gload_n<R1>(p, a0, (long long)M * in_rstride, pre_r, pre_i);
                 } else {
 #pragma unroll
                     for (int i = 0; i < R1; ++i) { pre_r[i] = T(0); pre_i[i] = T(0); }
@@ -361,7 +412,9 @@ struct PassKernel {
         }
 
         // ---- stage 1: global -> registers -> (twiddle, DFT) -> tile (or global when S == 1) ------
-        {
+        // The input layout is tested once, outside the task loop (see gload_n).
+        auto stage1 = [&](auto il_tag) {
+            constexpr int IL = decltype(il_tag)::value;
             constexpr int NTASK = M * C;
             constexpr int TRIPS1 = (NTASK + NT - 1) / NT;
 #pragma unroll((VARIANT & 4) ? TRIPS1 : 1)
@@ -384,8 +437,7 @@ struct PassKernel {
                     for (int i = 0; i < R1; ++i) { xr[i] = pre_r[i]; xi[i] = pre_i[i]; }
                 } else if (valid) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
-#pragma unroll
-                    for (int i = 0; i < R1; ++i) gload(p, a0 + (long long)(i * M) * in_rstride, xr[i], xi[i]);
+                    gload_n<R1, IL>(p, a0, (long long)M * in_rstride, xr, xi);
                 } else {
 #pragma unroll
                     for (int i = 0; i < R1; ++i) { xr[i] = T(0); xi[i] = T(0); }
@@ -418,17 +470,16 @@ struct PassKernel {
                     for (int k = 0; k < R1; ++k) tile[Addr::at(j * R1 + k, c)] = make_cx<T>(xr[k], xi[k]);
                 } else {
                     if (valid) {
-#pragma unroll
-                        for (int k = 0; k < R1; ++k) {
-                            long long idx;
-                            if constexpr (KIND == KIND_ROW) idx = out_base + (long long)c * p.out_bstride + k;
-                            else idx = out_base + (long long)k * out_kstride + c;
-                            gstore(p, idx, xr[k], xi[k]);
-                        }
+                        if constexpr (KIND == KIND_ROW) gstore_n<R1>(p, out_base + (long long)c * p.out_bstride, 1LL, xr, xi);
+                        else gstore_n<R1>(p, out_base + c, out_kstride, xr, xi);
                     }
                 }
             }
-        }
+        };
+        if constexpr (ASYNC || PRELOAD) stage1(std::integral_constant<int, 0>{});
+        else if (p.in_interleaved == 0) stage1(std::integral_constant<int, 0>{});
+        else if (p.in_interleaved == 1) stage1(std::integral_constant<int, 1>{});
+        else stage1(std::integral_constant<int, 2>{});
         // ---- stages 2..S -------------------------------------------------------------------------
         run_stages<1>(p, tile, out_base, out_kstride, rows_valid, tid);
     }

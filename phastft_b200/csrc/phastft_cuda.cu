@@ -147,7 +147,8 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
         v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());      // +20% over the plain build (tune5)
         v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 0, 16, 8, 8>());     // 512 threads: 20.0 vs 21.2 us at 2^20 (tune8)
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 32, 32>());       // two radix-32 stages: 19.2-19.5 vs 19.4-20.3 us at 2^20 (tune23/25)
+        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 70, 16, 8, 8>());    // id 70: the three-stage build (512 threads: 20.0 vs 21.2 us, tune8)
         v.push_back(make_entry_v<T, KIND, CH, 512, 0, 1, 0, 16, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 60, 16, 8, 8>());
     } else {
@@ -158,7 +159,8 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
         v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 0, 16, 8, 8>());
         v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 60, 16, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 0, 16, 8, 8>());
+        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 0, 0, 32, 32>());       // two radix-32 stages: 14.0 vs 15.3 us at 2^20 (tune25)
+        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 70, 16, 8, 8>());    // id 70: the three-stage build
         v.push_back(make_entry_v<T, KIND, CH, 512, 0, 1, 60, 16, 8, 8>());
     }
     // ---- alternates kept for re-tuning ------------------------------------------------------------------
@@ -174,6 +176,28 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 16, 8, 8>());
     v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 20, 16, 8, 8>());        // id 20: 256 threads
     v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 25, 8, 8, 16>());        // id 25
+    // ids 61-65: 1024-row tiles at half width (64 KB f64 / 32 KB f32), for interleaved intermediates
+    v.push_back(make_entry_v<T, KIND, CH, 256, 4, 1, 61, 16, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CH, 256, 7, 2, 62, 16, 8, 8>());       // register budget pinned to 2 CTAs/SM (150 regs and 1 CTA/SM otherwise)
+    v.push_back(make_entry_v<T, KIND, CH, 256, 7, 3, 67, 16, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CH, 256, 0, 2, 63, 16, 8, 8>());
+    v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 64, 4, 16, 16>());
+    v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 65, 16, 16, 4>());
+    v.push_back(make_entry_v<T, KIND, CH, 128, 0, 1, 66, 16, 8, 8>());
+    // id 32: radix-32 register stages -> 1024 and 512 rows with ONE shared-memory exchange
+    if constexpr (F64) {
+        v.push_back(make_entry_v<T, KIND, CH, 128, 0, 0, 32, 32, 32>());      // 168 regs, 64 KB tile: 3 CTAs/SM
+        v.push_back(make_entry_v<T, KIND, CH, 64, 0, 0, 32, 16, 32>());
+        v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 32, 16, 32>());
+        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 32, 16, 32>());
+        v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 34, 32, 16>());
+    } else {
+        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 0, 32, 32, 32>());
+        v.push_back(make_entry_v<T, KIND, CH, 128, 0, 0, 32, 16, 32>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 32, 16, 32>());
+        v.push_back(make_entry_v<T, KIND, CW, 512, 0, 0, 32, 16, 32>());
+        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 34, 32, 16>());
+    }
 }
 
 template <typename T>
@@ -345,7 +369,9 @@ struct Plan {
     mutable std::mutex mu;
     mutable T* ws_re = nullptr;
     mutable T* ws_im = nullptr;
-    mutable size_t ws_elems = 0;        // per array
+    mutable size_t ws_elems = 0;        // per array; ONE allocation of 2*ws_elems, ws_im = ws_re + ws_elems
+    int ws_il = -1;                     // layout of the intermediates between passes: 0 planar, 1 interleaved
+                                        // complex, -1 = interleaved for 3-pass plans and large batches (run_c2c)
     T* ws2_re = nullptr;                // 3-pass plans: L2-resident scratch for one k1 group (see run_c2c)
     T* ws2_im = nullptr;
     long long l2_group = 0;             // k1 values per group
@@ -362,7 +388,6 @@ struct Plan {
         DeviceGuard g(device);
         if (blob_dev) cudaFree(blob_dev);
         if (ws_re) cudaFree(ws_re);
-        if (ws_im) cudaFree(ws_im);
         if (fuse_bar) cudaFree(fuse_bar);
         if (ws2_re) cudaFree(ws2_re);
         if (ws2_im) cudaFree(ws2_im);
@@ -372,6 +397,16 @@ struct Plan {
         if (stream) cudaStreamDestroy(stream);
     }
 };
+
+// Layout of the intermediates between passes: planar (two halves of the workspace) or interleaved
+// complex.  Interleaved makes every access a 16-byte (f64) element, so a 64-byte run needs half as many
+// columns: the 1024-row middle tile of 2^25..2^26 shrinks from 128 KB to 64 KB and two CTAs share an SM
+// (2^26 f64 middle pass 646 -> 513 us, tools/tune25.py); streaming passes gain 2-9 % (tune24/25), single
+// L2-resident transforms lose 2-7 %, hence the automatic rule.  PHASTFT_WS_IL=0|1 forces a layout.
+inline int ws_interleaved_mode() {
+    const char* e = getenv("PHASTFT_WS_IL");
+    return e ? (atoi(e) != 0 ? 1 : 0) : -1;
+}
 
 // An explicit plan choice (PlannerMode::Tune tries several and keeps the fastest); consulted by
 // choose_factors / pick_kernel before the heuristics, like the PHASTFT_FACTORS / PHASTFT_PASS_C env overrides.
@@ -432,8 +467,8 @@ std::vector<int> choose_factors(int n) {
 // with 16; 2^20 f64 stays at 8 columns because its 1024-row tile holds only one CTA per SM).
 template <typename T>
 const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bool hbm_strided, bool l2_resident = false,
-                                  size_t rows_total = 0) {
-    int want_c = 0, want_variant = 0;
+                                  size_t rows_total = 0, int pref_c = 0, int pref_variant = 0) {
+    int want_c = pref_c, want_variant = pref_variant;
     auto nth = [&](const char* name, int& out) {
         if (const char* env = getenv(name)) {
             std::string sv(env);
@@ -518,6 +553,8 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
 
     std::vector<int> f = ln == 0 ? std::vector<int>{} : choose_factors<T>(ln);
     pl->num_passes = (int)f.size();
+    pl->ws_il = ws_interleaved_mode();
+    const bool il3 = pl->num_passes == 3 && pl->ws_il != 0;   // the middle pass reads and writes interleaved data
     // two-level W_N table
     pl->lo_bits = (ln + 1) / 2;
     const size_t n_lo = size_t(1) << pl->lo_bits, n_hi = size_t(1) << (ln - pl->lo_bits);
@@ -539,12 +576,15 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         // wide (128-byte) runs pay off once the signal no longer lives in L2; below that more, smaller CTAs win
         const bool big = ln >= 21;     // above 2^20 the passes are multi-wave streams, below single latency-bound waves
         const bool wide = (p == 0 || last) && big;
-        d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide, /*l2_resident=*/!big, /*rows_total=*/n >> f[p]);
+        // interleaved 1024-row middle pass: half-width (64-byte-run) tile, two CTAs per SM
+        const bool half_mid = il3 && p == 1 && f[p] == 10;
+        const int pref_c = half_mid ? TileC<T>::CH : 0, pref_v = half_mid ? 62 : 0;
+        d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide, /*l2_resident=*/!big, /*rows_total=*/n >> f[p], pref_c, pref_v);
         // batched calls are multi-wave streams whatever N is: wide runs only where the rows of a tile are
         // far apart in memory (>= 64 KiB: first-pass loads, last-pass stores of large N), else 64-byte runs
         const size_t far_stride = (kind == KIND_COL ? (size_t(1) << d.log2B) : (n >> f[p])) * sizeof(T);
         const bool wide_b = (p == 0 || last) && far_stride >= (size_t(64) << 10);
-        d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b);
+        d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b, false, 0, pref_c, pref_v);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
         if (p > 0) {
             d.has_tw = 1;
@@ -629,8 +669,8 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
     if (pl->alt_row.k)
         CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.k->smem));
     if (pl->num_passes >= 2) {
-        CUDA_TRY(cudaMalloc(&pl->ws_re, n * sizeof(T)));
-        CUDA_TRY(cudaMalloc(&pl->ws_im, n * sizeof(T)));
+        CUDA_TRY(cudaMalloc(&pl->ws_re, 2 * n * sizeof(T)));
+        pl->ws_im = pl->ws_re + n;
         pl->ws_elems = n;
     }
     if (pl->num_passes == 3) {
@@ -692,6 +732,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                      std::to_string(k->C) + " NT=" + std::to_string(k->NT);
             }
         }
+        if (pl->num_passes >= 2) s += pl->ws_il == 1 ? " [interleaved intermediates]" : pl->ws_il == 0 ? " [planar intermediates]" : "";
         if (pl->fused) s += " [fused launch, grid " + std::to_string(pl->fused_grid) + "]";
         if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
         pl->description = s;
@@ -703,6 +744,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
 // =================================================================================================
 // execution
 // =================================================================================================
+
 template <typename T>
 struct Io {
     const T* in_re; const T* in_im;
@@ -844,10 +886,9 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
         CUDA_TRY(cudaStreamSynchronize(stream));
         CUDA_TRY(cudaDeviceSynchronize());
         if (pl.ws_re) cudaFree(pl.ws_re);
-        if (pl.ws_im) cudaFree(pl.ws_im);
         pl.ws_re = pl.ws_im = nullptr; pl.ws_elems = 0;
-        CUDA_TRY(cudaMalloc(&pl.ws_re, chunk * pl.n * sizeof(T)));
-        CUDA_TRY(cudaMalloc(&pl.ws_im, chunk * pl.n * sizeof(T)));
+        CUDA_TRY(cudaMalloc(&pl.ws_re, 2 * chunk * pl.n * sizeof(T)));
+        pl.ws_im = pl.ws_re + chunk * pl.n;
         pl.ws_elems = chunk * pl.n;
     }
     // Workspace reuse is ordered by the stream itself when consecutive calls use the same stream;
@@ -933,6 +974,8 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
         }
         return PHASTFT_OK;
     }
+    const bool many_call = batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
+    const int il = pl.ws_il >= 0 ? pl.ws_il : ((P == 3 || many_call) ? 1 : 0);
     for (size_t done = 0; done < batch; done += chunk) {
         const size_t nb = std::min(chunk, batch - done);
         for (int p = 0; p < P; ++p) {
@@ -945,6 +988,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
                 prm.in_interleaved = io.in_il;
             } else {
                 prm.in_re = pl.ws_re; prm.in_im = pl.ws_im; prm.in_bstride = (long long)pl.n;
+                prm.in_interleaved = il;
             }
             if (p == P - 1) {
                 prm.out_re = io.out_re + (io.out_il ? 2 : 1) * done * io.out_bstride;
@@ -954,6 +998,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
                 prm.scale = scale;
             } else {
                 prm.out_re = pl.ws_re; prm.out_im = pl.ws_im; prm.out_bstride = (long long)pl.n;
+                prm.out_interleaved = il;
             }
             if (pass_events && done == 0 && p == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
             int32_t st = launch_pass(pl, p, prm, nb, stream);
