@@ -379,6 +379,8 @@ struct Plan {
     mutable T* stage_im = nullptr;
     mutable size_t stage_elems = 0;
     mutable cudaStream_t stream = nullptr;   // used by the *_host entry points
+    mutable cudaStream_t stream_h2d = nullptr;   // copy streams of the pipelined batch host path (created lazily)
+    mutable cudaStream_t stream_d2h = nullptr;
     mutable cudaEvent_t ws_free = nullptr;   // orders workspace reuse across streams
     mutable cudaStream_t ws_last_stream = nullptr;
     mutable bool ws_used = false;
@@ -395,6 +397,8 @@ struct Plan {
         if (stage_im) cudaFree(stage_im);
         if (ws_free) cudaEventDestroy(ws_free);
         if (stream) cudaStreamDestroy(stream);
+        if (stream_h2d) cudaStreamDestroy(stream_h2d);
+        if (stream_d2h) cudaStreamDestroy(stream_d2h);
     }
 };
 
@@ -1144,6 +1148,11 @@ int32_t fft_oneshot(T* re, size_t len_re, T* im, size_t len_im, int direction, i
     return st;
 }
 
+// Host-resident batch, sharded over the plans' devices (contiguous ranges; no collective on
+// the data path).  Per device the shard moves through a three-slot pipeline -- H2D of chunk j+1, the FFTs of
+// chunk j and D2H of chunk j-1 run on three streams -- so both PCIe directions are busy at once; a chunk is
+// ~16 MiB per array (PHASTFT_HOST_CHUNK_MB).  Overlap needs page-locked host memory; pageable memory is
+// still correct, the copies just serialise.
 template <typename T>
 int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, size_t batch, size_t bstride, int direction) {
     if (!plans || num_plans <= 0 || !re || !im) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
@@ -1152,31 +1161,94 @@ int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, s
     for (int g = 0; g < num_plans; ++g)
         if (!plans[g] || plans[g]->n != n) return fail(PHASTFT_ERR_PLAN_MISMATCH);
     if (bstride < n) return fail(PHASTFT_ERR_INVALID_ARG, "batch_stride < N");
-    // contiguous ranges of transforms per device; no collective on the data path
-    std::vector<size_t> lo(num_plans + 1);
-    for (int g = 0; g <= num_plans; ++g) lo[g] = batch * g / num_plans;
+    if (batch == 0) return PHASTFT_OK;
+    constexpr int NSLOT = 3;
+    size_t chunk_mb = 16;
+    if (const char* e = getenv("PHASTFT_HOST_CHUNK_MB")) { long v = atol(e); if (v > 0) chunk_mb = (size_t)v; }
+    const size_t per_chunk = std::max<size_t>(1, (chunk_mb << 20) / (n * sizeof(T)));   // transforms per chunk
+    struct Shard {
+        const Plan<T>* pl; size_t lo, nb, chunks; size_t slot_elems;
+        cudaEvent_t h2d_done[NSLOT], fft_done[NSLOT], d2h_done[NSLOT];
+        bool ev = false;
+    };
+    std::vector<Shard> sh(num_plans);
+    auto cleanup = [&]() {
+        for (auto& s : sh)
+            if (s.ev) {
+                DeviceGuard guard(s.pl->device);
+                for (int k = 0; k < NSLOT; ++k) { cudaEventDestroy(s.h2d_done[k]); cudaEventDestroy(s.fft_done[k]); cudaEventDestroy(s.d2h_done[k]); }
+                s.ev = false;
+            }
+    };
+    size_t max_chunks = 0;
     for (int g = 0; g < num_plans; ++g) {
-        const Plan<T>* pl = plans[g];
-        const size_t nb = lo[g + 1] - lo[g];
-        if (!nb) continue;
-        DeviceGuard guard(pl->device);
+        Shard& s = sh[g];
+        s.pl = plans[g];
+        s.lo = batch * g / num_plans;
+        s.nb = batch * (g + 1) / num_plans - s.lo;
+        const size_t pc = std::min(per_chunk, std::max<size_t>(1, s.nb));
+        s.chunks = (s.nb + pc - 1) / pc;
+        s.slot_elems = pc * n;
+        max_chunks = std::max(max_chunks, s.chunks);
+        if (!s.nb) continue;
+        DeviceGuard guard(s.pl->device);
         {
-            std::lock_guard<std::mutex> lock(pl->mu);
-            int32_t st = ensure_staging(pl, nb * n);
-            if (st) return st;
+            std::lock_guard<std::mutex> lock(s.pl->mu);
+            int32_t st = ensure_staging(s.pl, std::min<size_t>(NSLOT, s.chunks) * s.slot_elems);
+            if (st) { cleanup(); return st; }
+            if (!s.pl->stream_h2d) {
+                if (cudaStreamCreateWithFlags(&s.pl->stream_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+                    cudaStreamCreateWithFlags(&s.pl->stream_d2h, cudaStreamNonBlocking) != cudaSuccess) { cleanup(); return fail(PHASTFT_ERR_CUDA, "stream create"); }
+            }
         }
-        CUDA_TRY(cudaMemcpy2DAsync(pl->stage_re, n * sizeof(T), re + lo[g] * bstride, bstride * sizeof(T), n * sizeof(T), nb, cudaMemcpyHostToDevice, pl->stream));
-        CUDA_TRY(cudaMemcpy2DAsync(pl->stage_im, n * sizeof(T), im + lo[g] * bstride, bstride * sizeof(T), n * sizeof(T), nb, cudaMemcpyHostToDevice, pl->stream));
-        int32_t st = fft_dev(pl, pl->stage_re, pl->stage_im, direction, nb, n, pl->stream);
-        if (st) return st;
-        CUDA_TRY(cudaMemcpy2DAsync(re + lo[g] * bstride, bstride * sizeof(T), pl->stage_re, n * sizeof(T), n * sizeof(T), nb, cudaMemcpyDeviceToHost, pl->stream));
-        CUDA_TRY(cudaMemcpy2DAsync(im + lo[g] * bstride, bstride * sizeof(T), pl->stage_im, n * sizeof(T), n * sizeof(T), nb, cudaMemcpyDeviceToHost, pl->stream));
+        for (int k = 0; k < NSLOT; ++k) {
+            cudaEventCreateWithFlags(&s.h2d_done[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&s.fft_done[k], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&s.d2h_done[k], cudaEventDisableTiming);
+        }
+        s.ev = true;
+    }
+    // issue chunk j of every device before chunk j+1 of any, so all devices stream concurrently
+    int32_t st = PHASTFT_OK;
+    for (size_t j = 0; j < max_chunks && !st; ++j) {
+        for (int g = 0; g < num_plans && !st; ++g) {
+            Shard& s = sh[g];
+            if (j >= s.chunks) continue;
+            const Plan<T>* pl = s.pl;
+            DeviceGuard guard(pl->device);
+            const size_t pc = s.slot_elems / n;
+            const size_t first = s.lo + j * pc;
+            const size_t cnt = std::min(pc, s.lo + s.nb - first);
+            const int slot = (int)(j % NSLOT);
+            T* d_re = pl->stage_re + (size_t)slot * s.slot_elems;
+            T* d_im = pl->stage_im + (size_t)slot * s.slot_elems;
+            T* h_re = re + first * bstride;
+            T* h_im = im + first * bstride;
+            auto ok = [&](cudaError_t e) { if (e != cudaSuccess && !st) st = fail(PHASTFT_ERR_CUDA, cudaGetErrorString(e)); return e == cudaSuccess; };
+            if (j >= NSLOT) ok(cudaStreamWaitEvent(pl->stream_h2d, s.d2h_done[slot], 0));     // the slot's previous result has left
+            ok(cudaMemcpy2DAsync(d_re, n * sizeof(T), h_re, bstride * sizeof(T), n * sizeof(T), cnt, cudaMemcpyHostToDevice, pl->stream_h2d));
+            ok(cudaMemcpy2DAsync(d_im, n * sizeof(T), h_im, bstride * sizeof(T), n * sizeof(T), cnt, cudaMemcpyHostToDevice, pl->stream_h2d));
+            ok(cudaEventRecord(s.h2d_done[slot], pl->stream_h2d));
+            ok(cudaStreamWaitEvent(pl->stream, s.h2d_done[slot], 0));
+            if (!st) st = fft_dev(pl, d_re, d_im, direction, cnt, n, pl->stream);
+            ok(cudaEventRecord(s.fft_done[slot], pl->stream));
+            ok(cudaStreamWaitEvent(pl->stream_d2h, s.fft_done[slot], 0));
+            ok(cudaMemcpy2DAsync(h_re, bstride * sizeof(T), d_re, n * sizeof(T), n * sizeof(T), cnt, cudaMemcpyDeviceToHost, pl->stream_d2h));
+            ok(cudaMemcpy2DAsync(h_im, bstride * sizeof(T), d_im, n * sizeof(T), n * sizeof(T), cnt, cudaMemcpyDeviceToHost, pl->stream_d2h));
+            ok(cudaEventRecord(s.d2h_done[slot], pl->stream_d2h));
+        }
     }
     for (int g = 0; g < num_plans; ++g) {
+        if (!sh[g].nb) continue;
         DeviceGuard guard(plans[g]->device);
-        CUDA_TRY(cudaStreamSynchronize(plans[g]->stream));
+        cudaError_t e1 = cudaStreamSynchronize(plans[g]->stream_h2d);
+        cudaError_t e2 = cudaStreamSynchronize(plans[g]->stream);
+        cudaError_t e3 = cudaStreamSynchronize(plans[g]->stream_d2h);
+        for (cudaError_t e : {e1, e2, e3})
+            if (e != cudaSuccess && !st) st = fail(PHASTFT_ERR_CUDA, cudaGetErrorString(e));
     }
-    return PHASTFT_OK;
+    cleanup();
+    return st;
 }
 
 // ---- PlannerMode::Tune (planner.rs:25-32: "benchmarks both paths at plan time, picks whichever is faster";

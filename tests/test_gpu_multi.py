@@ -39,3 +39,34 @@ def test_tables_export_import_roundtrip():
     a, b = re.copy(), im.copy(); pf.fft_32_dit_with_planner(a, b, pf.Direction.Forward, p0)
     c, d = re.copy(), im.copy(); pf.fft_32_dit_with_planner(c, d, pf.Direction.Forward, p1)
     assert np.array_equal(a, c) and np.array_equal(b, d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned", [False, True])
+def test_batch_host_pipeline_chunks_and_stride(pinned, monkeypatch):
+    """The host-resident batch goes through a 3-slot H2D / FFT / D2H pipeline: many small chunks, a ragged last
+    chunk, a batch stride larger than N (gaps must stay untouched), pageable and page-locked memory."""
+    import torch
+    import phastft_b200 as pf
+    n, batch, stride = 1 << 14, 37, (1 << 14) + 24
+    monkeypatch.setenv("PHASTFT_HOST_CHUNK_MB", "1")          # 1 MiB / (2^14 * 8 B) = 8 transforms per chunk -> 5 chunks
+    rng = np.random.default_rng(99)
+    total = (batch - 1) * stride + n
+    t_re = torch.from_numpy(rng.uniform(-1, 1, total)); t_im = torch.from_numpy(rng.uniform(-1, 1, total))
+    if pinned:
+        t_re, t_im = t_re.pin_memory(), t_im.pin_memory()
+    re, im = t_re.numpy(), t_im.numpy()
+    ref_re, ref_im = re.copy(), im.copy()
+    planner = pf.PlannerDit64(n, 0)
+    pf.fft_dit_batch_sharded(re, im, pf.Direction.Forward, [planner], batch, batch_stride=stride)
+    tol = 4 * 2.0 ** -52 * 14
+    for b in range(batch):
+        want = np.fft.fft(ref_re[b * stride:b * stride + n] + 1j * ref_im[b * stride:b * stride + n])
+        got = re[b * stride:b * stride + n] + 1j * im[b * stride:b * stride + n]
+        assert np.max(np.abs(got - want)) / np.max(np.abs(want)) <= tol, b
+        if b + 1 < batch:   # the gap between signals is not part of any transform
+            assert np.array_equal(re[b * stride + n:(b + 1) * stride], ref_re[b * stride + n:(b + 1) * stride])
+            assert np.array_equal(im[b * stride + n:(b + 1) * stride], ref_im[b * stride + n:(b + 1) * stride])
+    # and back: forward then reverse is the identity
+    pf.fft_dit_batch_sharded(re, im, pf.Direction.Reverse, [planner], batch, batch_stride=stride)
+    assert np.max(np.abs(re - ref_re)) <= 64 * tol and np.max(np.abs(im - ref_im)) <= 64 * tol
