@@ -343,3 +343,32 @@ def test_tune_mode_correct_and_not_slower(dt, log_n):
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1)
     assert time_it(tuned) <= 1.15 * time_it(plain)
+
+
+# --- the layout of the intermediates between passes is an internal choice: both must be right -------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("ws_il", ["0", "1"])
+@pytest.mark.parametrize("log_n", [13, 18, 20, 21, 22])
+def test_forced_intermediate_layout(dt, ws_il, log_n, monkeypatch):
+    """PHASTFT_WS_IL=0|1 forces planar / interleaved-complex intermediates (default: interleaved for 3-pass plans
+    and large batches).  Same tolerance either way, forward and reverse, single and batched."""
+    import torch
+    pf, O = _pf(), _O()
+    monkeypatch.setenv("PHASTFT_WS_IL", ws_il)
+    n = 1 << log_n
+    planner = planner_for(dt, n)
+    assert ("interleaved intermediates" in planner.describe()) == (ws_il == "1")
+    re0, im0 = O.gen_random_signal(n, dt, seed=77 + log_n)
+    o_re, o_im = re0.copy(), im0.copy()
+    O.fft_dit(o_re, o_im, O.FORWARD)
+    g_re, g_im = re0.copy(), im0.copy()
+    fft_with_planner(dt)(g_re, g_im, pf.Direction.Forward, planner)
+    assert rel_linf(g_re, g_im, o_re, o_im) <= tol(dt, n), planner.describe()
+    fft_with_planner(dt)(g_re, g_im, pf.Direction.Reverse, planner)
+    assert rel_linf(g_re, g_im, re0, im0) <= 2 * tol(dt, n)
+    batch = 3
+    d_re = torch.from_numpy(np.tile(re0, batch)).cuda(); d_im = torch.from_numpy(np.tile(im0, batch)).cuda()
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, planner, batch)
+    b_re, b_im = d_re.cpu().numpy(), d_im.cpu().numpy()
+    for b in range(batch):
+        assert rel_linf(b_re[b * n:(b + 1) * n], b_im[b * n:(b + 1) * n], o_re, o_im) <= tol(dt, n), b
