@@ -184,6 +184,8 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 64, 4, 16, 16>());
     v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 65, 16, 16, 4>());
     v.push_back(make_entry_v<T, KIND, CH, 128, 0, 1, 66, 16, 8, 8>());
+    // (four-stage 64-register builds of this tile -- 8x8x4x4, 4x4x8x8, 8x8x8x2, 2x8x8x8 at 512 threads, 32 warps/SM --
+    //  measured 582-615 us against 508 us for id 62 on the 2^26 middle pass, tools/tune28.py: not kept)
     // id 32: radix-32 register stages -> 1024 and 512 rows with ONE shared-memory exchange
     if constexpr (F64) {
         v.push_back(make_entry_v<T, KIND, CH, 128, 0, 0, 32, 32, 32>());      // 168 regs, 64 KB tile: 3 CTAs/SM
