@@ -224,6 +224,18 @@ const std::vector<KernelEntry<T>>& registry() {
         v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 70, 8, 16, 16>());
         v.push_back(make_entry_v<T, KIND_ROW, 1, 64, 0, 0, 70, 4, 16, 16>());
         v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 70, 16, 16>());
+        // ids 80/81: one-CTA kernels for BATCHES of small transforms (tools/tune29.py, 2^24 points per call):
+        // 4..16 points split in two stages so the lanes of a warp run along the row (coalesced) instead of one
+        // row per lane -- n=16 f64 259 -> 121 us; 512 / 1024 points with ONE shared-memory exchange (32x16, 32x32)
+        // -- f32 n=1024 86 -> 52 us; 2048 points as 16x16x8.  The losing candidates (8x8x8 at 2 and 4 rows per CTA,
+        // 16x32, 32x8x8, 2x32x32, 32x16x8, 4x32x32) are not kept.
+        v.push_back(make_entry_v<T, KIND_ROW, 64, 128, 0, 0, 80, 2, 2>());
+        v.push_back(make_entry_v<T, KIND_ROW, 64, 128, 0, 0, 80, 2, 4>());
+        v.push_back(make_entry_v<T, KIND_ROW, 32, 128, 0, 0, 80, 4, 4>());
+        v.push_back(make_entry_v<T, KIND_ROW, 16, 64, 0, 0, 81, 4, 4>());
+        v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 81, 32, 16>());
+        v.push_back(make_entry_v<T, KIND_ROW, 2, 64, 0, 0, 81, 32, 32>());
+        v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 81, 16, 16, 8>());
 
         // ---- first / middle passes (KIND_COL) and last pass (KIND_TRANS) ---------------------------
         add_strided_kernels<T, KIND_COL>(v);
@@ -532,10 +544,26 @@ const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bo
 // f32 2^11 3.4 vs 2.2 TB/s, f64 2^11/2^12 3.4 vs 2.9 TB/s) while a lone transform prefers the default.
 template <typename T>
 const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
-    const bool use16 = R == 256 || R == 2048 || (R == 4096 && sizeof(T) == 8);
-    if (!use16) return dflt;
+    if (const char* env = getenv("PHASTFT_ROW_VARIANT")) {        // re-tuning override
+        const int want = atoi(env);
+        for (const auto& e : registry<T>())
+            if (e.kind == KIND_ROW && e.R == R && e.variant == want) return &e;
+    }
+    // measured per size (tools/tune19.py, tools/tune29.py); 0 = the lone-transform kernel is also the best batch kernel
+    const bool f64 = sizeof(T) == 8;
+    int want = 0;
+    switch (R) {
+        case 4: case 8: want = 80; break;
+        case 16: want = f64 ? 80 : 81; break;
+        case 256: want = 70; break;
+        case 512: case 1024: want = 81; break;
+        case 2048: want = f64 ? 81 : 70; break;
+        case 4096: want = f64 ? 70 : 0; break;
+        default: break;
+    }
+    if (!want) return dflt;
     for (const auto& e : registry<T>())
-        if (e.kind == KIND_ROW && e.R == R && e.variant == 70) return &e;
+        if (e.kind == KIND_ROW && e.R == R && e.variant == want) return &e;
     return dflt;
 }
 

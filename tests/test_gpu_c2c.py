@@ -372,3 +372,29 @@ def test_forced_intermediate_layout(dt, ws_il, log_n, monkeypatch):
     b_re, b_im = d_re.cpu().numpy(), d_im.cpu().numpy()
     for b in range(batch):
         assert rel_linf(b_re[b * n:(b + 1) * n], b_im[b * n:(b + 1) * n], o_re, o_im) <= tol(dt, n), b
+
+
+# --- large batches of small transforms take their own one-CTA kernels (two-stage 4/8/16-point, 32x16, 32x32, ...) ---
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 256, 512, 1024, 2048, 4096])
+def test_large_batch_of_small_transforms(dt, n):
+    """batch * N >= 2^21 switches a plan to its batch kernels; a ragged batch count leaves a partly filled last CTA."""
+    import torch
+    pf = _pf()
+    batch = (1 << 21) // n + 37
+    rng = np.random.default_rng(n)
+    re_h = rng.uniform(-1, 1, (batch, n)).astype(dt); im_h = rng.uniform(-1, 1, (batch, n)).astype(dt)
+    planner = planner_for(dt, n)
+    d_re = torch.from_numpy(re_h.reshape(-1).copy()).cuda(); d_im = torch.from_numpy(im_h.reshape(-1).copy()).cuda()
+    guard_re = torch.full((n,), 7.0, dtype=d_re.dtype, device="cuda")       # memory right after the batch must stay untouched
+    d_all_re = torch.cat([d_re, guard_re]); d_all_im = torch.cat([d_im, guard_re])
+    pf.fft_dit_batch(d_all_re[:batch * n], d_all_im[:batch * n], pf.Direction.Forward, planner, batch)
+    got = (d_all_re[:batch * n].cpu().numpy().astype(np.float64) + 1j * d_all_im[:batch * n].cpu().numpy().astype(np.float64)).reshape(batch, n)
+    want = np.fft.fft(re_h.astype(np.float64) + 1j * im_h.astype(np.float64), axis=-1)
+    err = np.max(np.abs(got - want), axis=-1) / np.max(np.abs(want), axis=-1)
+    assert float(err.max()) <= tol(dt, n), (planner.describe(), int(err.argmax()), float(err.max()))
+    assert bool((d_all_re[batch * n:] == 7.0).all()) and bool((d_all_im[batch * n:] == 7.0).all())
+    # reverse brings the batch back
+    pf.fft_dit_batch(d_all_re[:batch * n], d_all_im[:batch * n], pf.Direction.Reverse, planner, batch)
+    back = d_all_re[:batch * n].cpu().numpy().reshape(batch, n)
+    assert float(np.max(np.abs(back.astype(np.float64) - re_h))) <= 8 * tol(dt, n)

@@ -10,7 +10,7 @@ dev = torch.device("cuda", 0)
 
 
 def prof(sfx, n_log, env, batch=1, reps=10):
-    for k in ("PHASTFT_FACTORS", "PHASTFT_TILE_C", "PHASTFT_ASYNC", "PHASTFT_L2_GROUP_MB", "PHASTFT_VARIANT", "PHASTFT_PASS_C", "PHASTFT_PASS_VARIANT", "PHASTFT_WS_IL"):
+    for k in ("PHASTFT_FACTORS", "PHASTFT_TILE_C", "PHASTFT_ASYNC", "PHASTFT_L2_GROUP_MB", "PHASTFT_VARIANT", "PHASTFT_PASS_C", "PHASTFT_PASS_VARIANT", "PHASTFT_WS_IL", "PHASTFT_ROW_VARIANT"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     n = 1 << n_log
