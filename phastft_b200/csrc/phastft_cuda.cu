@@ -612,7 +612,9 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const bool wide = (p == 0 || last) && big;
         // interleaved 1024-row middle pass: half-width (64-byte-run) tile, two CTAs per SM
         const bool half_mid = il3 && p == 1 && f[p] == 10;
-        const int pref_c = half_mid ? TileC<T>::CH : 0, pref_v = half_mid ? 62 : 0;
+        // lone 2^11-point f32 transform in one CTA: 8x16x16 (3.7 us) beats 4x8x8x8 (4.4 us), tools/tune30.py
+        const bool row2048_f32 = kind == KIND_ROW && f[p] == 11 && sizeof(T) == 4;
+        const int pref_c = half_mid ? TileC<T>::CH : 0, pref_v = half_mid ? 62 : row2048_f32 ? 70 : 0;
         d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide, /*l2_resident=*/!big, /*rows_total=*/n >> f[p], pref_c, pref_v);
         // batched calls are multi-wave streams whatever N is: wide runs only where the rows of a tile are
         // far apart in memory (>= 64 KiB: first-pass loads, last-pass stores of large N), else 64-byte runs

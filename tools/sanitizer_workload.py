@@ -9,14 +9,16 @@ import phastft_b200 as pf
 import torch
 rng = np.random.default_rng(0)
 for dt, P, f in ((np.float64, pf.PlannerDit64, pf.fft_64_dit_with_planner), (np.float32, pf.PlannerDit32, pf.fft_32_dit_with_planner)):
-    for n in (1, 2, 8, 64, 256, 1024, 4096, 1 << 13, 1 << 15, 1 << 16, 1 << 18, 1 << 21):
+    for n in (1, 2, 8, 64, 256, 1024, 2048, 4096, 1 << 13, 1 << 15, 1 << 16, 1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22):
         re = rng.uniform(-1, 1, n).astype(dt); im = rng.uniform(-1, 1, n).astype(dt)
         pl = P(n)
         ref = np.fft.fft(re.astype(np.float64) + 1j * im)
         f(re, im, pf.Direction.Forward, pl)
         err = np.max(np.abs(re + 1j * im - ref)) / max(np.max(np.abs(ref)), 1e-30)
         assert err < (1e-13 if dt == np.float64 else 1e-5), (dt, n, err)
-    for n, b in ((256, 40), (2048, 9), (4096, 5), (1 << 16, 40)):
+    # small batches, then batches with batch * N >= 2^21 (their own kernels, interleaved intermediates, ragged last CTA)
+    for n, b in ((256, 40), (2048, 9), (4096, 5), (1 << 16, 40), (4, (1 << 19) + 3), (8, (1 << 18) + 5), (16, (1 << 17) + 7),
+                 (512, 4099), (1024, 2051), (2048, 1027), (4096, 515), (1 << 14, 131), (1 << 21, 2)):
         pl = P(n)
         tdt = torch.float64 if dt == np.float64 else torch.float32
         d_re = torch.rand(n * b, dtype=tdt, device="cuda"); d_im = torch.rand(n * b, dtype=tdt, device="cuda")
@@ -32,4 +34,27 @@ for n in (4, 64, 4096, 1 << 15):
     assert np.max(np.abs(ore + 1j * oim - np.fft.rfft(x))) < 1e-10
     y = np.zeros(n); pf.c2r_fft_f64(ore, oim, y)
     assert np.max(np.abs(y - x)) < 1e-12
+# host-resident batch through the 3-slot copy / compute pipeline (5 chunks, ragged tail, strided), both layouts forced
+import os
+os.environ["PHASTFT_HOST_CHUNK_MB"] = "1"
+n, b, stride = 1 << 14, 37, (1 << 14) + 24
+tot = (b - 1) * stride + n
+h_re = torch.from_numpy(rng.uniform(-1, 1, tot)).pin_memory(); h_im = torch.from_numpy(rng.uniform(-1, 1, tot)).pin_memory()
+a_re, a_im = h_re.numpy(), h_im.numpy()
+x = np.stack([a_re[i * stride:i * stride + n] + 1j * a_im[i * stride:i * stride + n] for i in range(b)])
+pf.fft_dit_batch_sharded(a_re, a_im, pf.Direction.Forward, [pf.PlannerDit64(n)], b, batch_stride=stride)
+got = np.stack([a_re[i * stride:i * stride + n] + 1j * a_im[i * stride:i * stride + n] for i in range(b)])
+assert np.max(np.abs(got - np.fft.fft(x, axis=1))) / np.max(np.abs(x)) < 1e-11
+for il in ("0", "1"):
+    os.environ["PHASTFT_WS_IL"] = il
+    for n in (1 << 13, 1 << 21):
+        re = rng.uniform(-1, 1, n); im = rng.uniform(-1, 1, n)
+        ref = np.fft.fft(re + 1j * im)
+        pf.fft_64_dit_with_planner(re, im, pf.Direction.Forward, pf.PlannerDit64(n))
+        assert np.max(np.abs(re + 1j * im - ref)) / np.max(np.abs(ref)) < 1e-13
+os.environ.pop("PHASTFT_WS_IL")
+z = (rng.uniform(-1, 1, 1 << 15) + 1j * rng.uniform(-1, 1, 1 << 15)).astype(np.complex128)
+ref = np.fft.ifft(z)
+pf.fft_64_interleaved(z, pf.Direction.Reverse)
+assert np.max(np.abs(z - ref)) / np.max(np.abs(ref)) < 1e-13
 print("sanitizer workload ok")
