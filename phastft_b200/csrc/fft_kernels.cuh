@@ -490,131 +490,7 @@ struct PassKernel {
         run_stages<1>(p, tile, out_base, out_kstride, rows_valid, tid);
     }
 
-    // ---- persistent, double-buffered COL pass ----------------------------------------------------------
-    // One CTA per SM loops over tiles b, b + grid, b + 2*grid, ...: while tile t runs its stages out of one
-    // shared-memory buffer, the cp.async copies of tile t + grid land in the other one, so the HBM reads of
-    // the next tile overlap the FP64 phases of the current one inside a single CTA (a plain launch only gets
-    // that overlap from co-resident CTAs).  Stage 1 reads its operands from shared memory instead of global.
-    static constexpr size_t SMEM_BYTES_PERSISTENT = sizeof(cx<T>) * (size_t)(2 * TILE_ELEMS + M + R1);
-    struct ColAddr { long long in_base, out_base, rstride; uint32_t kp0, bcol0; };
-    static __device__ __forceinline__ ColAddr col_addr(const PassParams<T>& p, unsigned tile_index) {
-        const int tilesB = 1 << (p.log2B - LOG2C);
-        const unsigned blk = tile_index + (unsigned)p.blk_offset;
-        const int bt = blk & (tilesB - 1);
-        const int rest = blk >> (p.log2B - LOG2C);
-        const int a = rest & ((1 << p.log2A) - 1);
-        const int batch = rest >> p.log2A;
-        const long long off = ((long long)a << (LOG2R + p.log2B)) + ((long long)bt << LOG2C);
-        ColAddr r;
-        r.in_base = (long long)batch * p.in_bstride + off;
-        r.out_base = (long long)batch * p.out_bstride + off;
-        r.rstride = 1LL << p.log2B;
-        r.kp0 = a & ((1u << p.log2Rprev) - 1u);
-        r.bcol0 = (uint32_t)bt << LOG2C;
-        return r;
-    }
-    static __device__ __forceinline__ void issue_tile(const PassParams<T>& p, const ColAddr& ad, cx<T>* tile, int tid) {
-        constexpr int NTASK0 = M * C;
-#pragma unroll
-        for (int t = tid; t < NTASK0; t += NT) {
-            const int c = t % C, mp = t / C;
-            const int j = rev_tail<RL>(mp);
-            const long long a0 = ad.in_base + c + (long long)mp * ad.rstride;
-#pragma unroll
-            for (int i = 0; i < R1; ++i) {
-                const long long idx = a0 + (long long)(i * M) * ad.rstride;
-                cx<T>* dst = tile + Addr::at(j * R1 + i, c);
-                if (p.in_interleaved) {
-                    if constexpr (sizeof(cx<T>) == 16) cp_async_cg16(dst, reinterpret_cast<const cx<T>*>(p.in_re) + idx);
-                    else cp_async<2 * (int)sizeof(T)>(dst, reinterpret_cast<const cx<T>*>(p.in_re) + idx);
-                } else {
-                    cp_async<(int)sizeof(T)>(&dst->x, p.in_re + idx);
-                    cp_async<(int)sizeof(T)>(&dst->y, p.in_im + idx);
-                }
-            }
-        }
-    }
-    static __device__ __forceinline__ void body_persistent(const PassParams<T>& p, unsigned ntiles) {
-        static_assert(KIND == KIND_COL && S >= 2, "persistent mode is for multi-stage COL passes");
-        extern __shared__ __align__(16) unsigned char smem_raw[];
-        cx<T>* buf0 = reinterpret_cast<cx<T>*>(smem_raw);
-        cx<T>* buf1 = buf0 + TILE_ELEMS;
-        cx<T>* s_um = buf1 + TILE_ELEMS;
-        cx<T>* s_g = s_um + M;
-        const int tid = (int)threadIdx.x;
-        unsigned t = blockIdx.x;
-        int cur = 0;
-        if (t < ntiles) issue_tile(p, col_addr(p, t), buf0, tid);
-        cp_async_commit();
-        const bool swap_in = p.in_interleaved == 2;
-        for (; t < ntiles; t += gridDim.x) {
-            cx<T>* tile = cur ? buf1 : buf0;
-            const unsigned tn = t + gridDim.x;
-            if (tn < ntiles) issue_tile(p, col_addr(p, tn), cur ? buf0 : buf1, tid);
-            cp_async_commit();
-            const ColAddr ad = col_addr(p, t);
-            // per-tile inter-pass twiddle factors (see body()); their table lookups overlap the copies in flight
-            cx<T> vreg = make_cx<T>(T(1), T(0));
-            const bool has_tw = p.has_tw;
-            if (has_tw) {
-                for (int mp = tid; mp < M; mp += NT) {
-                    uint32_t e = (ad.kp0 * (uint32_t)mp) << p.log2B;
-                    s_um[mp] = to_cx<T>(p.tw2.get(e << p.tw_shift));
-                }
-                constexpr int LOG2M = ilog2_c(M);
-                for (int q = tid; q < R1; q += NT) {
-                    uint32_t e = (ad.kp0 * (uint32_t)q) << (LOG2M + p.log2B);
-                    s_g[q] = to_cx<T>(p.tw2.get(e << p.tw_shift));
-                }
-                const int c = tid % C;
-                vreg = to_cx<T>(p.tw2.get((ad.kp0 * (ad.bcol0 + (uint32_t)c)) << p.tw_shift));
-            }
-            cp_async_wait_group<1>();          // everything but the newest group (the next tile) has landed
-            __syncthreads();
-            // ---- stage 1 out of shared memory, in place
-            constexpr int NTASK = M * C;
-#pragma unroll
-            for (int q = tid; q < NTASK; q += NT) {
-                const int c = q % C, mp = q / C;
-                const int j0 = rev_tail<RL>(mp);
-                T xr[R1], xi[R1];
-#pragma unroll
-                for (int i = 0; i < R1; ++i) {
-                    cx<T> v = tile[Addr::at(j0 * R1 + i, c)];
-                    xr[i] = swap_in ? v.y : v.x;
-                    xi[i] = swap_in ? v.x : v.y;
-                }
-                if (has_tw) {
-                    cx<T> pt = cmul<T>(s_um[mp], vreg);
-                    {
-                        T a = xr[0], b = xi[0];
-                        xr[0] = fma_t(-b, pt.y, a * pt.x);
-                        xi[0] = fma_t(b, pt.x, a * pt.y);
-                    }
-#pragma unroll
-                    for (int i = 1; i < R1; ++i) {
-                        cx<T> w = cmul<T>(pt, s_g[i]);
-                        T a = xr[i], b = xi[i];
-                        xr[i] = fma_t(-b, w.y, a * w.x);
-                        xi[i] = fma_t(b, w.x, a * w.y);
-                    }
-                }
-                Dft<T, R1>::run(xr, xi);
-#pragma unroll
-                for (int k = 0; k < R1; ++k) tile[Addr::at(j0 * R1 + k, c)] = make_cx<T>(xr[k], xi[k]);
-            }
-            run_stages<1>(p, tile, ad.out_base, ad.rstride, C, tid);
-            __syncthreads();                   // every thread is done with this buffer (and with s_um / s_g)
-            cur ^= 1;
-        }
-        cp_async_wait_all();
-    }
 };
-
-template <typename T, class RL, int C, int NT, int VARIANT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) fft_pass_persistent_kernel(const __grid_constant__ PassParams<T> p, unsigned ntiles) {
-    PassKernel<T, RL, C, NT, KIND_COL, 0, VARIANT>::body_persistent(p, ntiles);
-}
 
 template <typename T, class RL, int C, int NT, int KIND, int ASYNC, int VARIANT = 0, int MINB = 0>
 __global__ void __launch_bounds__(NT, MINB) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {

@@ -71,7 +71,6 @@ struct DeviceGuard {
 template <typename T>
 struct KernelEntry {
     int kind, R, C, NT, first_radix, stages, async, variant;
-    int persistent = 0;        // fft_pass_persistent_kernel: grid = SMs x occupancy, takes (params, ntiles)
     size_t smem;
     const void* fn;
     std::string radices;
@@ -89,23 +88,6 @@ KernelEntry<T> make_entry_v() {
     const int rs[] = {Rs...};
     for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
     if (ID) e.radices += ",v" + std::to_string(ID);
-    return e;
-}
-
-// persistent double-buffered COL pass (experimental ids >= 90)
-template <typename T, int C, int NT, int VARIANT, int MINB, int ID, int... Rs>
-KernelEntry<T> make_entry_p() {
-    using RL = RadixList<Rs...>;
-    using PK = PassKernel<T, RL, C, NT, KIND_COL, 0, VARIANT>;
-    static_assert(PK::SMEM_BYTES_PERSISTENT <= 227 * 1024, "two tile buffers exceed the 227 KB shared memory of an sm_100 CTA");
-    KernelEntry<T> e;
-    e.kind = KIND_COL; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.async = 0; e.variant = ID;
-    e.persistent = 1;
-    e.smem = PK::SMEM_BYTES_PERSISTENT;
-    e.fn = reinterpret_cast<const void*>(&fft_pass_persistent_kernel<T, RL, C, NT, VARIANT, MINB>);
-    const int rs[] = {Rs...};
-    for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
-    e.radices += ",persistent,v" + std::to_string(ID);
     return e;
 }
 
@@ -204,20 +186,9 @@ void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
     v.push_back(make_entry_v<T, KIND, CH, 128, 0, 1, 66, 16, 8, 8>());
     // (four-stage 64-register builds of this tile -- 8x8x4x4, 4x4x8x8, 8x8x8x2, 2x8x8x8 at 512 threads, 32 warps/SM --
     //  measured 582-615 us against 508 us for id 62 on the 2^26 middle pass, tools/tune28.py: not kept)
-    // ids 90-93: persistent double-buffered half-width 1024-row COL pass (tools/tune31.py)
-    if constexpr (KIND == KIND_COL) {
-        v.push_back(make_entry_p<T, CH, 512, 0, 1, 90, 16, 8, 8>());
-        v.push_back(make_entry_p<T, CH, 256, 0, 1, 91, 16, 8, 8>());
-        v.push_back(make_entry_p<T, CH, 256, 1, 1, 92, 16, 8, 8>());
-        v.push_back(make_entry_p<T, CH, 256, 0, 1, 93, 16, 16, 4>());
-    }
-    // ids 94-97: quarter-width (one 32-byte sector per row, interleaved f64) 1024-row tiles: 32 KB, 4-6 CTAs per SM
-    if constexpr (KIND == KIND_COL) {
-        v.push_back(make_entry_v<T, KIND, CH / 2, 128, 7, 4, 94, 16, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH / 2, 256, 7, 2, 95, 16, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH / 2, 64, 0, 0, 96, 32, 32>());
-        v.push_back(make_entry_v<T, KIND, CH / 2, 128, 0, 4, 97, 16, 16, 4>());
-    }
+    // (a persistent double-buffered build of this pass -- one CTA per SM, cp.async prefetch of the next tile under the
+    //  current tile's stages -- and quarter-width 32 KB tiles at 4-6 CTAs/SM were built and measured: 779-818 us and
+    //  669-901 us against 505 us for id 62 on the 2^26 f64 middle pass; see profiles/r01_tuning.md. Removed again.)
     // id 32: radix-32 register stages -> 1024 and 512 rows with ONE shared-memory exchange
     if constexpr (F64) {
         v.push_back(make_entry_v<T, KIND, CH, 128, 0, 0, 32, 32, 32>());      // 168 regs, 64 KB tile: 3 CTAs/SM
@@ -835,17 +806,6 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
     unsigned long long blocks = 0;
     int32_t st = prepare_pass(pl, p, base, batch, k1_lo, k1_cnt, prm, k, blocks);
     if (st) return st;
-    if (k->persistent) {
-        unsigned ntiles = (unsigned)blocks;
-        int occ = 1, sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, pl.device);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k->fn, k->NT, k->smem) != cudaSuccess || occ < 1) occ = 1;
-        const unsigned grid = (unsigned)std::min<unsigned long long>(blocks, (unsigned long long)sms * occ);
-        void* pargs[] = {&prm, &ntiles};
-        CUDA_TRY(cudaLaunchKernel(k->fn, dim3(grid), dim3(k->NT), pargs, k->smem, stream));
-        g_launches.fetch_add(1, std::memory_order_relaxed);
-        return PHASTFT_OK;
-    }
     void* args[] = {&prm};
     static const bool use_pdl = [] { const char* e = getenv("PHASTFT_PDL"); return e ? atoi(e) != 0 : false; }();   // measured: no gain at 2^20, -10% at 2^24+ (tune8)
     if (use_pdl) {
