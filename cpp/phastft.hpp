@@ -114,8 +114,8 @@ inline void fft_64_dit_with_planner(std::vector<double>& reals, std::vector<doub
     fft_64_dit_with_planner_and_opts(reals, imags, d, p, Options::guess_options(reals.size()));
 }
 inline void fft_64_dit(std::vector<double>& reals, std::vector<double>& imags, Direction d) {
-    PlannerDit64 p(reals.size());                       // lib.rs:181: a planner per call
-    fft_64_dit_with_planner(reals, imags, d, p);
+    // lib.rs:181: a planner per call; the library keeps the latest one for the next same-size call
+    check(phastft_fft_dit_f64_oneshot(reals.data(), reals.size(), imags.data(), imags.size(), (int)d, 0));
 }
 inline void fft_32_dit_with_planner_and_opts(std::vector<float>& reals, std::vector<float>& imags, Direction d, const PlannerDit32& p, const Options&) {
     check(detail::Api<float>::fft_host(p.raw(), reals.data(), reals.size(), imags.data(), imags.size(), (int)d));
@@ -124,8 +124,7 @@ inline void fft_32_dit_with_planner(std::vector<float>& reals, std::vector<float
     fft_32_dit_with_planner_and_opts(reals, imags, d, p, Options::guess_options(reals.size()));
 }
 inline void fft_32_dit(std::vector<float>& reals, std::vector<float>& imags, Direction d) {
-    PlannerDit32 p(reals.size());
-    fft_32_dit_with_planner(reals, imags, d, p);
+    check(phastft_fft_dit_f32_oneshot(reals.data(), reals.size(), imags.data(), imags.size(), (int)d, 0));
 }
 
 // ---- r2c / c2r (algorithms/r2c.rs:521-895) --------------------------------------------------------------

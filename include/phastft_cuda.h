@@ -41,6 +41,10 @@ PHASTFT_API const char* phastft_version(void);
 PHASTFT_API int32_t phastft_device_count(int* count);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
 PHASTFT_API uint64_t phastft_launch_count(void);
+/* The *_oneshot entry points (a planner per call, lib.rs:180 / r2c.rs:522,696) keep their most recent plan per
+ * precision and reuse it when the next call has the same size and device; this releases those plans and their
+ * device buffers. */
+PHASTFT_API void phastft_oneshot_cache_clear(void);
 
 /* ---- options.rs:10-43 : Options / guess_options ------------------------------------------
  * Kept for source compatibility.  On the GPU both fields are hints with no effect: there is

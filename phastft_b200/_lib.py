@@ -103,6 +103,9 @@ def check(code: int):
         raise PhastFTPanic(code, (lib.phastft_last_error() or b"").decode())
 
 
+lib.phastft_oneshot_cache_clear.argtypes = []
+lib.phastft_oneshot_cache_clear.restype = None
+
 lib.phastft_plan_factorization.argtypes = [_sz, _ci, C.POINTER(_ci), C.POINTER(_ci)]
 lib.phastft_plan_factorization.restype = _i32
 
@@ -115,7 +118,7 @@ def plan_factorization(n: int, precision_bits: int = 64):
     return [f[i] for i in range(k.value)]
 
 
-GLOBAL_SYMBOLS = ["phastft_plan_factorization", "phastft_last_error", "phastft_version", "phastft_launch_count", "phastft_device_count",
+GLOBAL_SYMBOLS = ["phastft_oneshot_cache_clear", "phastft_plan_factorization", "phastft_last_error", "phastft_version", "phastft_launch_count", "phastft_device_count",
                   "phastft_options_default", "phastft_options_guess"]
 
 for _name, (_args, _res) in SIGNATURES.items():

@@ -223,10 +223,13 @@ def _fft_dit_with_planner(sfx, dtype, reals, imags, direction, planner, opts=Non
 
 def _fft_dit(sfx, dtype, planner_cls, reals, imags, direction, device=0):
     # lib.rs:180-183: a planner per call
-    n = reals.numel() if _is_torch(reals) else reals.size
-    if _is_torch(reals):
-        device = reals.device.index or 0
-    planner = planner_cls(n, device)
+    if not _is_torch(reals):
+        # host slices: the library's one-shot entry (it keeps the latest plan for the next same-size call)
+        pr, nr = _np_ptr(reals, dtype, True)
+        pi, ni = _np_ptr(imags, dtype, True)
+        check(fn("phastft_fft_dit_{s}_oneshot", sfx)(pr, nr, pi, ni, int(direction), int(device)))
+        return
+    planner = planner_cls(reals.numel(), reals.device.index or 0)
     _fft_dit_with_planner(sfx, dtype, reals, imags, direction, planner)
 
 
@@ -406,6 +409,12 @@ def _dev_of(a, device):
 
 def r2c_fft_f64(input_re, output_re, output_im, device: int = 0) -> None:
     """r2c.rs:521: PlannerR2c64::new(input_re.len()) then the planner path."""
+    if not _is_torch(input_re):
+        px, nx = _np_ptr(input_re, np.float64, False)
+        pr, nr = _np_ptr(output_re, np.float64, True)
+        pi, ni = _np_ptr(output_im, np.float64, True)
+        check(fn("phastft_r2c_{s}_oneshot", "f64")(px, nx, pr, nr, pi, ni, int(device)))
+        return
     _r2c_with_planner("f64", np.float64, input_re, output_re, output_im, PlannerR2c64(_len(input_re), _dev_of(input_re, device)))
 
 
@@ -416,6 +425,12 @@ def r2c_fft_f64_with_planner(input_re, output_re, output_im, planner: PlannerR2c
 
 def c2r_fft_f64(input_re, input_im, output, device: int = 0) -> None:
     """r2c.rs:695: PlannerR2c64::new(output.len())"""
+    if not _is_torch(output):
+        pr, nr = _np_ptr(input_re, np.float64, False)
+        pi, ni = _np_ptr(input_im, np.float64, False)
+        po, no = _np_ptr(output, np.float64, True)
+        check(fn("phastft_c2r_{s}_oneshot", "f64")(pr, nr, pi, ni, po, no, int(device)))
+        return
     _c2r_with_planner("f64", np.float64, input_re, input_im, output, PlannerR2c64(_len(output), _dev_of(output, device)))
 
 
@@ -431,6 +446,12 @@ def c2r_fft_f64_with_planner_and_scratch(input_re, input_im, output, planner: Pl
 
 def r2c_fft_f32(input_re, output_re, output_im, device: int = 0) -> None:
     """r2c.rs:598"""
+    if not _is_torch(input_re):
+        px, nx = _np_ptr(input_re, np.float32, False)
+        pr, nr = _np_ptr(output_re, np.float32, True)
+        pi, ni = _np_ptr(output_im, np.float32, True)
+        check(fn("phastft_r2c_{s}_oneshot", "f32")(px, nx, pr, nr, pi, ni, int(device)))
+        return
     _r2c_with_planner("f32", np.float32, input_re, output_re, output_im, PlannerR2c32(_len(input_re), _dev_of(input_re, device)))
 
 
@@ -441,6 +462,12 @@ def r2c_fft_f32_with_planner(input_re, output_re, output_im, planner: PlannerR2c
 
 def c2r_fft_f32(input_re, input_im, output, device: int = 0) -> None:
     """r2c.rs:804"""
+    if not _is_torch(output):
+        pr, nr = _np_ptr(input_re, np.float32, False)
+        pi, ni = _np_ptr(input_im, np.float32, False)
+        po, no = _np_ptr(output, np.float32, True)
+        check(fn("phastft_c2r_{s}_oneshot", "f32")(pr, nr, pi, ni, po, no, int(device)))
+        return
     _c2r_with_planner("f32", np.float32, input_re, input_im, output, PlannerR2c32(_len(output), _dev_of(output, device)))
 
 

@@ -420,7 +420,7 @@ struct PassKernel {
         // ---- stage 1: global -> registers -> (twiddle, DFT) -> tile (or global when S == 1) ------
         // The input layout is tested once, outside the task loop (see gload_n).
         auto stage1 = [&](auto il_tag) {
-            constexpr int IL = decltype(il_tag)::value;
+            [[maybe_unused]] constexpr int IL = decltype(il_tag)::value;
             constexpr int NTASK = M * C;
             constexpr int TRIPS1 = (NTASK + NT - 1) / NT;
 #pragma unroll((VARIANT & 4) ? TRIPS1 : 1)
@@ -428,7 +428,7 @@ struct PassKernel {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
                 T xr[R1], xi[R1];
-                const bool valid = (KIND != KIND_ROW) || (c < rows_valid);
+                [[maybe_unused]] const bool valid = (KIND != KIND_ROW) || (c < rows_valid);
                 if constexpr (ASYNC) {
                     const int j0 = rev_tail<RL>(mp);
                     const bool swap = p.in_interleaved == 2;

@@ -1171,16 +1171,37 @@ int32_t fft_interleaved_host(const Plan<T>* pl, T* sig, size_t len_complex, int 
     return PHASTFT_OK;
 }
 
+// One-shot calls build their planner per call, like the reference (lib.rs:180-183).  Building is cheap, but
+// allocating and releasing the workspace and staging buffers is not (130 ms per 2^24 f64 call), so the most
+// recent one-shot plan per precision is kept and reused when the next call has the same size and device;
+// phastft_oneshot_cache_clear() releases it.  The cache entry is held under its lock for the whole call.
+template <class P>
+struct OneShotCache {
+    std::mutex mu;
+    P* plan = nullptr;          // intentionally not freed at process exit (the CUDA context may be gone by then)
+    size_t n = 0;
+    int device = -1;
+    void clear() {
+        std::lock_guard<std::mutex> lock(mu);
+        delete plan;
+        plan = nullptr; n = 0; device = -1;
+    }
+};
+template <typename T> OneShotCache<Plan<T>>& oneshot_c2c_cache() { static auto* c = new OneShotCache<Plan<T>>(); return *c; }
+
 template <typename T>
 int32_t fft_oneshot(T* re, size_t len_re, T* im, size_t len_im, int direction, int device) {
-    // lib.rs:180-183: PlannerDit::new(reals.len()) then the with_planner path
     if (!is_pow2(len_re)) return fail(PHASTFT_ERR_NOT_POW2);
-    Plan<T>* pl = nullptr;
-    int32_t st = build_plan<T>(len_re, device, &pl);
-    if (st) return st;
-    st = fft_host(pl, re, len_re, im, len_im, direction);
-    delete pl;
-    return st;
+    auto& c = oneshot_c2c_cache<T>();
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (!c.plan || c.n != len_re || c.device != device) {
+        delete c.plan;
+        c.plan = nullptr; c.n = 0; c.device = -1;
+        int32_t st = build_plan<T>(len_re, device, &c.plan);
+        if (st) return st;
+        c.n = len_re; c.device = device;
+    }
+    return fft_host(c.plan, re, len_re, im, len_im, direction);
 }
 
 // Host-resident batch, sharded over the plans' devices (contiguous ranges; no collective on
@@ -1562,6 +1583,21 @@ int32_t c2r_host(const PlanR2c<T>* pl, const T* ire, size_t len_ire, const T* ii
     return PHASTFT_OK;
 }
 
+template <typename T> OneShotCache<PlanR2c<T>>& oneshot_r2c_cache() { static auto* c = new OneShotCache<PlanR2c<T>>(); return *c; }
+// caller holds c.mu
+template <typename T>
+int32_t oneshot_r2c_plan(OneShotCache<PlanR2c<T>>& c, size_t n, int device, PlanR2c<T>** out) {
+    if (!c.plan || c.n != n || c.device != device) {
+        delete c.plan;
+        c.plan = nullptr; c.n = 0; c.device = -1;
+        int32_t st = build_plan_r2c<T>(n, device, &c.plan);
+        if (st) return st;
+        c.n = n; c.device = device;
+    }
+    *out = c.plan;
+    return PHASTFT_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -1576,6 +1612,13 @@ extern "C" {
 
 const char* phastft_last_error(void) { return g_last_error.c_str(); }
 const char* phastft_version(void) { return "phastft_cuda 0.1.0 (sm_100a)"; }
+void phastft_oneshot_cache_clear(void) {
+    oneshot_c2c_cache<double>().clear();
+    oneshot_c2c_cache<float>().clear();
+    oneshot_r2c_cache<double>().clear();
+    oneshot_r2c_cache<float>().clear();
+}
+
 uint64_t phastft_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int32_t phastft_device_count(int* count) {
     if (!count) return fail(PHASTFT_ERR_INVALID_ARG, "count == NULL");
@@ -1673,12 +1716,12 @@ void phastft_options_guess(size_t input_size, phastft_options* out) {
         return r2c_host<T>(AS_CR2C(T, p), in, lin, ore, lore, oim, loim);                                               \
     }                                                                                                                   \
     int32_t phastft_r2c_##SFX##_oneshot(const T* in, size_t lin, T* ore, size_t lore, T* oim, size_t loim, int dev) {   \
-        PlanR2c<T>* pl = nullptr;                                                                                       \
-        int32_t st = build_plan_r2c<T>(lin, dev, &pl); /* r2c.rs:522: PlannerR2c::new(input_re.len()) */                \
+        PlanR2c<T>* pl = nullptr; /* r2c.rs:522: PlannerR2c::new(input_re.len()), kept for the next same-size call */  \
+        auto& c = oneshot_r2c_cache<T>();                                                                               \
+        std::lock_guard<std::mutex> lock(c.mu);                                                                         \
+        int32_t st = oneshot_r2c_plan<T>(c, lin, dev, &pl);                                                             \
         if (st) return st;                                                                                              \
-        st = r2c_host<T>(pl, in, lin, ore, lore, oim, loim);                                                            \
-        delete pl;                                                                                                      \
-        return st;                                                                                                      \
+        return r2c_host<T>(pl, in, lin, ore, lore, oim, loim);                                                          \
     }                                                                                                                   \
     int32_t phastft_r2c_##SFX##_dev(const phastft_plan_r2c_##SFX* p, const T* in, T* ore, T* oim, void* s) {            \
         return r2c_dev<T>(AS_CR2C(T, p), in, ore, oim, (cudaStream_t)s);                                                \
@@ -1689,12 +1732,12 @@ void phastft_options_guess(size_t input_size, phastft_options* out) {
     }                                                                                                                   \
     int32_t phastft_c2r_##SFX##_oneshot(const T* ire, size_t lire, const T* iim, size_t liim, T* out, size_t lout,     \
                                         int dev) {                                                                      \
-        PlanR2c<T>* pl = nullptr;                                                                                       \
-        int32_t st = build_plan_r2c<T>(lout, dev, &pl); /* r2c.rs:696: PlannerR2c::new(output.len()) */                 \
+        PlanR2c<T>* pl = nullptr; /* r2c.rs:696: PlannerR2c::new(output.len()), kept for the next same-size call */    \
+        auto& c = oneshot_r2c_cache<T>();                                                                               \
+        std::lock_guard<std::mutex> lock(c.mu);                                                                         \
+        int32_t st = oneshot_r2c_plan<T>(c, lout, dev, &pl);                                                            \
         if (st) return st;                                                                                              \
-        st = c2r_host<T>(pl, ire, lire, iim, liim, out, lout, nullptr, 0, nullptr, 0);                                  \
-        delete pl;                                                                                                      \
-        return st;                                                                                                      \
+        return c2r_host<T>(pl, ire, lire, iim, liim, out, lout, nullptr, 0, nullptr, 0);                                \
     }                                                                                                                   \
     int32_t phastft_c2r_##SFX##_dev(const phastft_plan_r2c_##SFX* p, const T* ire, const T* iim, T* out, T* sre,        \
                                     T* sim, void* s) {                                                                  \

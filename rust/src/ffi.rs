@@ -13,6 +13,9 @@ pub struct phastft_options { pub multithreaded_bit_reversal: i32, pub smallest_p
 extern "C" {
     pub fn phastft_last_error() -> *const c_char;
     pub fn phastft_options_guess(input_size: usize, out: *mut phastft_options);
+    pub fn phastft_oneshot_cache_clear();
+    pub fn phastft_fft_dit_f64_oneshot(re: *mut f64, len_re: usize, im: *mut f64, len_im: usize, direction: c_int, device: c_int) -> i32;
+    pub fn phastft_fft_dit_f32_oneshot(re: *mut f32, len_re: usize, im: *mut f32, len_im: usize, direction: c_int, device: c_int) -> i32;
 
     pub fn phastft_plan_dit_f64_create(n: usize, device: c_int, mode: c_int, out: *mut *mut phastft_plan_dit_f64) -> i32;
     pub fn phastft_plan_dit_f32_create(n: usize, device: c_int, mode: c_int, out: *mut *mut phastft_plan_dit_f32) -> i32;

@@ -87,8 +87,10 @@ pub fn fft_64_dit_with_planner(reals: &mut [f64], imags: &mut [f64], direction: 
 
 /// `lib.rs:180` -- plans per call, like the reference.
 pub fn fft_64_dit(reals: &mut [f64], imags: &mut [f64], direction: Direction) {
-    let planner = PlannerDit64::new(reals.len());
-    fft_64_dit_with_planner(reals, imags, direction, &planner);
+    // a planner per call, as in the reference; the library keeps the latest one for the next same-size call
+    check(unsafe {
+        ffi::phastft_fft_dit_f64_oneshot(reals.as_mut_ptr(), reals.len(), imags.as_mut_ptr(), imags.len(), direction as i32, device())
+    });
 }
 
 /// `lib.rs:186`
@@ -99,8 +101,9 @@ pub fn fft_32_dit_with_planner(reals: &mut [f32], imags: &mut [f32], direction: 
 
 /// `lib.rs:223`
 pub fn fft_32_dit(reals: &mut [f32], imags: &mut [f32], direction: Direction) {
-    let planner = PlannerDit32::new(reals.len());
-    fft_32_dit_with_planner(reals, imags, direction, &planner);
+    check(unsafe {
+        ffi::phastft_fft_dit_f32_oneshot(reals.as_mut_ptr(), reals.len(), imags.as_mut_ptr(), imags.len(), direction as i32, device())
+    });
 }
 
 // ------------------------------------------------------------------------------------------------

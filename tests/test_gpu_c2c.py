@@ -398,3 +398,31 @@ def test_large_batch_of_small_transforms(dt, n):
     pf.fft_dit_batch(d_all_re[:batch * n], d_all_im[:batch * n], pf.Direction.Reverse, planner, batch)
     back = d_all_re[:batch * n].cpu().numpy().reshape(batch, n)
     assert float(np.max(np.abs(back.astype(np.float64) - re_h))) <= 8 * tol(dt, n)
+
+
+def test_oneshot_plan_cache():
+    """fft_64_dit builds a planner per call (lib.rs:180); the library keeps the latest one per precision and reuses it
+    for the next call of the same size.  Same results as the planner path, across a size change and a cache clear."""
+    pf = _pf()
+    from phastft_b200 import _lib
+    rng = np.random.default_rng(5)
+    for n in (1 << 12, 1 << 12, 1 << 17, 1 << 12):
+        re = rng.uniform(-1, 1, n); im = rng.uniform(-1, 1, n)
+        a, b = re.copy(), im.copy()
+        pf.fft_64_dit(a, b, pf.Direction.Forward)
+        c, d = re.copy(), im.copy()
+        pf.fft_64_dit_with_planner(c, d, pf.Direction.Forward, pf.PlannerDit64(n))
+        assert np.array_equal(a, c) and np.array_equal(b, d), n
+    _lib.lib.phastft_oneshot_cache_clear()
+    x = rng.uniform(-1, 1, 1 << 10)
+    ore = np.zeros(513); oim = np.zeros(513)
+    for _ in range(2):
+        pf.r2c_fft_f64(x, ore, oim)
+        assert np.max(np.abs(ore + 1j * oim - np.fft.rfft(x))) <= 1e-12
+    y = np.zeros(1 << 10)
+    pf.c2r_fft_f64(ore, oim, y)
+    assert np.max(np.abs(y - x)) <= 1e-13
+    _lib.lib.phastft_oneshot_cache_clear()
+    a = np.ones(8, np.float32); b = np.zeros(8, np.float32)
+    pf.fft_32_dit(a, b, pf.Direction.Forward)
+    assert a[0] == 8 and np.all(a[1:] == 0)
