@@ -23,6 +23,7 @@ reference): there it is the thing timed as the CPU baseline, never part of our a
 from __future__ import annotations
 
 import argparse
+import contextlib
 import ctypes as C
 import json
 import os
@@ -241,7 +242,8 @@ def workload_config(workload: str, gpus: int):
 def run_ours(args):
     import torch
     import __graft_entry__ as ge
-    ge.build()
+    with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
+        ge.build()
     import phastft_b200 as pf
     from phastft_b200 import _lib
     from phastft_b200.sharding import max_over_ranks, shard_range
