@@ -45,6 +45,12 @@ PHASTFT_API uint64_t phastft_launch_count(void);
  * precision and reuse it when the next call has the same size and device; this releases those plans and their
  * device buffers. */
 PHASTFT_API void phastft_oneshot_cache_clear(void);
+/* Page-lock / release a caller-owned host range (cudaHostRegister / cudaHostUnregister).  The *_host entry points
+ * accept any host memory, but copies from ordinary pageable memory run at ~13 GB/s against ~52 GB/s from page-locked
+ * memory (profiles/r01_host_call_cost.txt), and the batched host pipeline only overlaps with page-locked memory.
+ * Register long-lived buffers once; registration itself costs about as much as several copies. */
+PHASTFT_API int32_t phastft_host_register(void* host_ptr, size_t bytes);
+PHASTFT_API int32_t phastft_host_unregister(void* host_ptr);
 
 /* ---- options.rs:10-43 : Options / guess_options ------------------------------------------
  * Kept for source compatibility.  On the GPU both fields are hints with no effect: there is

@@ -103,6 +103,10 @@ def check(code: int):
         raise PhastFTPanic(code, (lib.phastft_last_error() or b"").decode())
 
 
+lib.phastft_host_register.argtypes = [_vp, _sz]
+lib.phastft_host_register.restype = _i32
+lib.phastft_host_unregister.argtypes = [_vp]
+lib.phastft_host_unregister.restype = _i32
 lib.phastft_oneshot_cache_clear.argtypes = []
 lib.phastft_oneshot_cache_clear.restype = None
 
@@ -118,7 +122,7 @@ def plan_factorization(n: int, precision_bits: int = 64):
     return [f[i] for i in range(k.value)]
 
 
-GLOBAL_SYMBOLS = ["phastft_oneshot_cache_clear", "phastft_plan_factorization", "phastft_last_error", "phastft_version", "phastft_launch_count", "phastft_device_count",
+GLOBAL_SYMBOLS = ["phastft_host_register", "phastft_host_unregister", "phastft_oneshot_cache_clear", "phastft_plan_factorization", "phastft_last_error", "phastft_version", "phastft_launch_count", "phastft_device_count",
                   "phastft_options_default", "phastft_options_guess"]
 
 for _name, (_args, _res) in SIGNATURES.items():

@@ -1612,6 +1612,16 @@ extern "C" {
 
 const char* phastft_last_error(void) { return g_last_error.c_str(); }
 const char* phastft_version(void) { return "phastft_cuda 0.1.0 (sm_100a)"; }
+int32_t phastft_host_register(void* host_ptr, size_t bytes) {
+    if (!host_ptr || !bytes) return fail(PHASTFT_ERR_INVALID_ARG, "NULL or empty range");
+    CUDA_TRY(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+    return PHASTFT_OK;
+}
+int32_t phastft_host_unregister(void* host_ptr) {
+    if (!host_ptr) return fail(PHASTFT_ERR_INVALID_ARG, "NULL pointer");
+    CUDA_TRY(cudaHostUnregister(host_ptr));
+    return PHASTFT_OK;
+}
 void phastft_oneshot_cache_clear(void) {
     oneshot_c2c_cache<double>().clear();
     oneshot_c2c_cache<float>().clear();

@@ -14,6 +14,8 @@ extern "C" {
     pub fn phastft_last_error() -> *const c_char;
     pub fn phastft_options_guess(input_size: usize, out: *mut phastft_options);
     pub fn phastft_oneshot_cache_clear();
+    pub fn phastft_host_register(host_ptr: *mut c_void, bytes: usize) -> i32;
+    pub fn phastft_host_unregister(host_ptr: *mut c_void) -> i32;
     pub fn phastft_fft_dit_f64_oneshot(re: *mut f64, len_re: usize, im: *mut f64, len_im: usize, direction: c_int, device: c_int) -> i32;
     pub fn phastft_fft_dit_f32_oneshot(re: *mut f32, len_re: usize, im: *mut f32, len_im: usize, direction: c_int, device: c_int) -> i32;
 

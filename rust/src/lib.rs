@@ -47,6 +47,16 @@ pub(crate) fn check(code: i32) {
     panic!("{msg}");
 }
 
+/// Page-lock a long-lived buffer so the host-slice calls copy at full PCIe speed (~52 GB/s instead of ~13 GB/s
+/// from pageable memory). Additive: the reference has no analogue. Undo with [`host_unregister`] before the
+/// buffer is freed.
+pub fn host_register<T>(buf: &mut [T]) {
+    check(unsafe { ffi::phastft_host_register(buf.as_mut_ptr() as *mut std::os::raw::c_void, std::mem::size_of_val(buf)) });
+}
+pub fn host_unregister<T>(buf: &mut [T]) {
+    check(unsafe { ffi::phastft_host_unregister(buf.as_mut_ptr() as *mut std::os::raw::c_void) });
+}
+
 pub(crate) fn device() -> i32 {
     std::env::var("PHASTFT_DEVICE").ok().and_then(|s| s.parse().ok()).unwrap_or(0)
 }
