@@ -19,6 +19,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <algorithm>
+#include <functional>
 #include <vector>
 
 #include "../../include/phastft_cuda.h"
@@ -48,6 +50,7 @@ int32_t fail(int32_t code, const std::string& detail = std::string()) {
                              _e == cudaErrorInvalidDevice)                                              \
                                 ? PHASTFT_ERR_NO_DEVICE                                                 \
                                 : PHASTFT_ERR_CUDA;                                                     \
+            (void)cudaGetLastError(); /* clear it: the next kernel-launch check must not see a stale error */ \
             return fail(_code, std::string(#expr) + " -> " + cudaGetErrorString(_e));                   \
         }                                                                                               \
     } while (0)
@@ -384,6 +387,7 @@ struct Plan {
     int lo_bits = 0;
     // workspace (multi-pass only) and host-API staging, grown lazily under `mu`
     mutable std::mutex mu;
+    mutable std::mutex host_mu;         // held for a whole *_host call: staging buffers + the plan's streams are per plan
     mutable T* ws_re = nullptr;
     mutable T* ws_im = nullptr;
     mutable size_t ws_elems = 0;        // per array; ONE allocation of 2*ws_elems, ws_im = ws_re + ws_elems
@@ -1135,6 +1139,7 @@ int32_t fft_host(const Plan<T>* pl, T* re, size_t len_re, T* im, size_t len_im, 
     if (st) return st;
     if (!re || !im) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
     DeviceGuard g(pl->device);
+    std::lock_guard<std::mutex> host_lock(pl->host_mu);   // planners are shared by reference between threads
     {
         std::lock_guard<std::mutex> lock(pl->mu);
         st = ensure_staging(pl, pl->n);
@@ -1157,6 +1162,7 @@ int32_t fft_interleaved_host(const Plan<T>* pl, T* sig, size_t len_complex, int 
     if (st) return st;
     if (!sig) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
     DeviceGuard g(pl->device);
+    std::lock_guard<std::mutex> host_lock(pl->host_mu);
     {
         std::lock_guard<std::mutex> lock(pl->mu);
         st = ensure_staging(pl, 2 * pl->n);
@@ -1218,6 +1224,14 @@ int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, s
         if (!plans[g] || plans[g]->n != n) return fail(PHASTFT_ERR_PLAN_MISMATCH);
     if (bstride < n) return fail(PHASTFT_ERR_INVALID_ARG, "batch_stride < N");
     if (batch == 0) return PHASTFT_OK;
+    std::vector<std::mutex*> locks;
+    for (int g = 0; g < num_plans; ++g) locks.push_back(&plans[g]->host_mu);
+    std::sort(locks.begin(), locks.end(), std::less<std::mutex*>());
+    locks.erase(std::unique(locks.begin(), locks.end()), locks.end());
+    if (locks.size() != (size_t)num_plans) return fail(PHASTFT_ERR_INVALID_ARG, "the same plan passed twice");
+    struct Unlock { std::vector<std::mutex*>& l; ~Unlock() { for (auto* m : l) m->unlock(); } };
+    for (auto* m : locks) m->lock();                         // address order: no deadlock between overlapping calls
+    Unlock unlock_all{locks};
     constexpr int NSLOT = 3;
     size_t chunk_mb = 16;
     if (const char* e = getenv("PHASTFT_HOST_CHUNK_MB")) { long v = atol(e); if (v > 0) chunk_mb = (size_t)v; }
@@ -1423,6 +1437,7 @@ struct PlanR2c {
     size_t hi_elems = 0, lo_elems = 0;
     int lo_bits = 0;
     mutable std::mutex mu;
+    mutable std::mutex host_mu;        // held for a whole *_host call (lock order: host_mu, then mu)
     mutable T* d_real = nullptr;       // host-API staging: N reals
     mutable T* d_spec_re = nullptr;    // N/2+1
     mutable T* d_spec_im = nullptr;
@@ -1540,6 +1555,7 @@ int32_t r2c_host(const PlanR2c<T>* pl, const T* in, size_t len_in, T* ore, size_
     if (len_oim != half + 1) return fail(PHASTFT_ERR_OUTPUT_IM_LEN);  // r2c.rs:549
     if (!in || !ore || !oim) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
     DeviceGuard g(pl->device);
+    std::lock_guard<std::mutex> host_lock(pl->host_mu);     // same lock as c2r_host: both use the plan's staging buffers
     std::lock_guard<std::mutex> lock(pl->mu);
     int32_t st = ensure_r2c_staging(pl);
     if (st) return st;
@@ -1569,8 +1585,9 @@ int32_t c2r_host(const PlanR2c<T>* pl, const T* ire, size_t len_ire, const T* ii
     if (!ire || !iim || !out) return fail(PHASTFT_ERR_INVALID_ARG, "NULL slice");
     DeviceGuard g(pl->device);
     cudaStream_t s = pl->inner->stream;
+    std::lock_guard<std::mutex> host_lock(pl->host_mu);     // whole call: the staging buffers and the stream are per plan
     {
-        std::lock_guard<std::mutex> lock(pl->mu);
+        std::lock_guard<std::mutex> lock(pl->mu);           // released before c2r_dev, which takes it for the plan-owned scratch
         int32_t st = ensure_r2c_staging(pl);
         if (st) return st;
     }

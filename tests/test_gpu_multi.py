@@ -70,20 +70,3 @@ def test_batch_host_pipeline_chunks_and_stride(pinned, monkeypatch):
     # and back: forward then reverse is the identity
     pf.fft_dit_batch_sharded(re, im, pf.Direction.Reverse, [planner], batch, batch_stride=stride)
     assert np.max(np.abs(re - ref_re)) <= 64 * tol and np.max(np.abs(im - ref_im)) <= 64 * tol
-
-
-@pytest.mark.gpu
-def test_host_register_roundtrip():
-    """phastft_host_register page-locks a caller-owned numpy array; results are unchanged, unregister succeeds,
-    and a second unregister reports a CUDA error through the status code."""
-    import phastft_b200 as pf
-    n = 1 << 16
-    rng = np.random.default_rng(3)
-    re = rng.uniform(-1, 1, n); im = rng.uniform(-1, 1, n)
-    want = np.fft.fft(re + 1j * im)
-    pf.host_register(re); pf.host_register(im)
-    pf.fft_64_dit(re, im, pf.Direction.Forward)
-    pf.host_unregister(re); pf.host_unregister(im)
-    assert np.max(np.abs(re + 1j * im - want)) / np.max(np.abs(want)) <= 4 * 2.0 ** -52 * 16
-    with pytest.raises(pf.PhastFTPanic):
-        pf.host_unregister(re)
