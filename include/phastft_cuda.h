@@ -83,6 +83,11 @@ PHASTFT_API size_t phastft_plan_dit_f32_size(const phastft_plan_dit_f32* plan);
 PHASTFT_API const char* phastft_plan_dit_f64_describe(const phastft_plan_dit_f64* plan);
 PHASTFT_API const char* phastft_plan_dit_f32_describe(const phastft_plan_dit_f32* plan);
 
+/* Sizes the plan's device workspace for calls of up to `batch` transforms now (the *_dev entry points otherwise
+ * grow it on the first larger call, which synchronises the device and is an error inside a CUDA-graph capture). */
+PHASTFT_API int32_t phastft_plan_dit_f64_reserve(const phastft_plan_dit_f64* plan, size_t batch);
+PHASTFT_API int32_t phastft_plan_dit_f32_reserve(const phastft_plan_dit_f32* plan, size_t batch);
+
 /* Host-only planning logic (no device needed): the pass decomposition N = 2^f0 * 2^f1 [* 2^f2] the
  * planner uses for `num_points` (one CTA per transform when *num_passes == 1; 0 passes for N == 1).
  * log2_factors must hold 3 ints. */
@@ -90,7 +95,10 @@ PHASTFT_API int32_t phastft_plan_factorization(size_t num_points, int precision_
 
 /* Planner-table blob (multi-GPU init): rank 0 exports its tables into a
  * device buffer, the host framework broadcasts that buffer once (ncclBroadcast /
- * torch.distributed.broadcast), every other rank imports it.  No per-call collectives. */
+ * torch.distributed.broadcast), every other rank imports it.  No per-call collectives.
+ * The blob starts with a 256-byte layout header (size, precision, pass sizes, each pass's tile width and first
+ * radix): import / broadcast return PHASTFT_ERR_PLAN_MISMATCH when the receiving plan was built with a different
+ * decomposition (PlannerMode::Tune or a PHASTFT_* override on one rank only) instead of installing foreign tables. */
 PHASTFT_API size_t phastft_plan_dit_f64_tables_bytes(const phastft_plan_dit_f64* plan);
 PHASTFT_API size_t phastft_plan_dit_f32_tables_bytes(const phastft_plan_dit_f32* plan);
 PHASTFT_API int32_t phastft_plan_dit_f64_tables_export(const phastft_plan_dit_f64* plan, void* dst_dev, void* stream);

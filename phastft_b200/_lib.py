@@ -77,6 +77,7 @@ SIGNATURES = {
     "phastft_plan_dit_{s}_destroy": ([_vp], None),
     "phastft_plan_dit_{s}_size": ([_vp], _sz),
     "phastft_plan_dit_{s}_describe": ([_vp], C.c_char_p),
+    "phastft_plan_dit_{s}_reserve": ([_vp, _sz], _i32),
     "phastft_plan_dit_{s}_tables_bytes": ([_vp], _sz),
     "phastft_plan_dit_{s}_tables_export": ([_vp, _vp, _vp], _i32),
     "phastft_plan_dit_{s}_tables_import": ([_vp, _vp, _vp], _i32),

@@ -127,6 +127,11 @@ class _PlannerDit:
         return fn("phastft_plan_dit_{s}_describe", self._sfx)(self._h).decode()
 
     # planner-table blob, for the one init-time broadcast of a multi-GPU job
+    def reserve(self, batch: int) -> None:
+        """Size the device workspace for calls of up to `batch` transforms now (otherwise the first larger call grows
+        it, synchronising the device -- an error inside a CUDA-graph capture)."""
+        check(fn("phastft_plan_dit_{s}_reserve", self._sfx)(self._h, int(batch)))
+
     def tables_bytes(self) -> int:
         return int(fn("phastft_plan_dit_{s}_tables_bytes", self._sfx)(self._h))
 

@@ -57,6 +57,9 @@ struct PassParams {
     const cx<T>* __restrict__ tw_stage;  // W_R^e, e < R           (stage twiddles)
     const cx<T>* __restrict__ tw_wc;     // KIND_TRANS, 2-pass plans: W_L^(c*m), [c][m] layout
     T scale;                       // multiplied into the stored result (1/N for the inverse)
+    // cluster exchange (XCH = 1 producer only): the consuming pass's tile is [CB rows][P2 points]
+    int xch_log2P2;                // log2 of the consumer's row length (= its R)
+    int xch_log2CB;                // log2 of the consumer's rows per CTA (= its C)
 };
 
 // Shared-memory tile addressing (units: complex elements).
@@ -90,27 +93,37 @@ struct TileAddr {
 // ---------------------------------------------------------------------------------------------
 // The pass kernel.
 // ---------------------------------------------------------------------------------------------
-// cp.async helpers (LDGSTS): global -> shared without staging through registers
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gsrc), "n"(BYTES) : "memory");
+// Cluster exchange helpers (thread-block clusters + distributed shared memory, sm_90+):
+//   cluster_sync()        barrier.cluster arrive(release) + wait(acquire) by every thread of every CTA of the cluster
+//   st_cluster(addr, v)   store into the shared memory of CTA `rank` of the cluster (mapa + st.shared::cluster)
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// 16-byte copies that bypass L1 (streaming data that is read exactly once)
-__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned map_to_rank(unsigned smem_addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster(unsigned addr, const double2& v) {
+    asm volatile("st.shared::cluster.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.x), "d"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cluster(unsigned addr, const float2& v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// ASYNC = 1: stage 1 does not load global memory into registers; instead every thread fires
-// cp.async copies for the WHOLE tile straight into its (digit-reversed) shared-memory slots at
-// kernel entry, the inter-pass twiddle tables are built while those copies are in flight, and
-// stage 1 then runs out of shared memory like the later stages.  All of a CTA's input bytes are in
-// flight at once, independent of the register budget.
-template <typename T, class RL, int C, int NT, int KIND, int ASYNC = 0, int VARIANT = 0>
+// XCH (cluster exchange role of this pass inside fft_cluster2_kernel, see there):
+//   0  plain pass: global memory in, global memory out
+//   1  producer (KIND_COL): the LAST stage does not store to global memory; every thread keeps its results in
+//      registers across a cluster barrier and then scatters them into the shared-memory tiles of the CTAs that own
+//      the rows in the next pass, in the layout [row c'][t] that pass's global loads would have read
+//   2  consumer (KIND_TRANS): stage 1 reads that tile instead of global memory (all threads first, then a
+//      __syncthreads, then the tile is overwritten in the pass's own layout)
+template <typename T, class RL, int C, int NT, int KIND, int XCH = 0, int VARIANT = 0>
 struct PassKernel {
     static constexpr int S = RL::S;
     static constexpr int R = RL::R();
@@ -123,7 +136,9 @@ struct PassKernel {
     static constexpr int TILE_ELEMS = (S >= 2) ? R * C : 0;
     static constexpr int G_ELEMS = (KIND == KIND_TRANS) ? C * R1 : R1;
     static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)(TILE_ELEMS + M + G_ELEMS);
-    static_assert(!ASYNC || (S >= 2 && KIND != KIND_ROW), "the async variant needs a shared-memory tile");
+    static_assert(XCH == 0 || S >= 2, "an exchanging pass needs a shared-memory tile");
+    static_assert(XCH != 1 || KIND == KIND_COL, "the producer of a cluster exchange is a COL pass");
+    static_assert(XCH != 2 || KIND == KIND_TRANS, "the consumer of a cluster exchange is a TRANS pass");
 
     // ---- global element access -------------------------------------------------------------
     static __device__ __forceinline__ void gload(const PassParams<T>& p, long long idx, T& re, T& im) {
@@ -248,6 +263,23 @@ struct PassKernel {
             if constexpr (!LAST) {
 #pragma unroll
                 for (int k = 0; k < RAD; ++k) tile[Addr::at(base + k * NS, c)] = make_cx<T>(xr[k], xi[k]);
+            } else if constexpr (XCH == 1) {
+                // last stage of the producing pass of a cluster exchange.  Output row h = m + k*NS of this CTA's column
+                // tcol belongs, in the next pass, to CTA h / CB of the cluster, which wants it at [h % CB][tcol] of its tile
+                // (the layout its global loads would have read from the workspace).  All tiles of the cluster are still
+                // being read by this very stage, so: results stay in registers, cluster barrier, then the scatter.
+                // Lanes run along c, so one store instruction writes 32 consecutive elements of one destination row.
+                static_assert(TRIPS == 1 && NTASK == NT, "the exchanging stage must be a single trip: one task per thread");
+                cluster_sync();
+                const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+                const unsigned tcol = (unsigned)out_base + (unsigned)c;     // body() passes the tile's first column in out_base
+                const unsigned cb_mask = (1u << p.xch_log2CB) - 1u;
+#pragma unroll
+                for (int k = 0; k < RAD; ++k) {
+                    const unsigned h = (unsigned)(m + k * NS);
+                    const unsigned off = ((h & cb_mask) << p.xch_log2P2) + tcol;
+                    st_cluster(map_to_rank(tile_s + off * (unsigned)sizeof(cx<T>), h >> p.xch_log2CB), make_cx<T>(xr[k], xi[k]));
+                }
             } else {
                 // last stage: g == 0, natural-order outputs kr = m + k*NS
                 if (KIND == KIND_ROW && c >= tile_rows_valid) continue;
@@ -314,6 +346,7 @@ struct PassKernel {
             out_kstride = in_rstride;
             kp0 = a & ((1u << p.log2Rprev) - 1u);
             bcol0 = (uint32_t)bt << LOG2C;
+            if constexpr (XCH == 1) out_base = (long long)bcol0;   // no global output: the last stage wants the tile's first column
         } else if constexpr (KIND == KIND_TRANS) {
             // rows of the tile: a(c) = (k0 + c) * rest_n + rest, rest_n = A / R1
             const int log2restn = p.log2A - p.log2R1;
@@ -342,41 +375,23 @@ struct PassKernel {
             out_kstride = 1;
         }
 
-        // ---- ASYNC: put the whole tile in flight before anything else --------------------------------
-        if constexpr (ASYNC) {
-            constexpr int NTASK0 = M * C;
-#pragma unroll 1
-            for (int t = tid; t < NTASK0; t += NT) {
-                int c, mp;
-                if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
-                const int j = rev_tail<RL>(mp);
-                const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
-#pragma unroll
-                for (int i = 0; i < R1; ++i) {
-                    const long long idx = a0 + (long long)(i * M) * in_rstride;
-                    cx<T>* dst = tile + Addr::at(j * R1 + i, c);
-                    if (p.in_interleaved) {
-                        cp_async<2 * (int)sizeof(T)>(dst, reinterpret_cast<const cx<T>*>(p.in_re) + idx);
-                    } else {
-                        cp_async<(int)sizeof(T)>(&dst->x, p.in_re + idx);
-                        cp_async<(int)sizeof(T)>(&dst->y, p.in_im + idx);
-                    }
-                }
-            }
-            cp_async_commit();
-        }
-
         // ---- PRELOAD: when every thread owns exactly one stage-1 task, issue its global loads NOW so
         // they are in flight while the twiddle tables below are built (their two-level lookups are two
         // dependent L2 round trips that would otherwise sit in front of the first data load).
-        constexpr bool PRELOAD = !ASYNC && (M * C <= NT);
+        constexpr bool PRELOAD = (M * C <= NT);
+        static_assert(XCH != 2 || PRELOAD, "the consumer's stage 1 must be a single trip (every thread holds its task's inputs across the barrier)");
         T pre_r[PRELOAD ? R1 : 1], pre_i[PRELOAD ? R1 : 1];
         if constexpr (PRELOAD) {
             const int t = tid;
             if (t < M * C) {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
-                if ((KIND != KIND_ROW) || (c < rows_valid)) {
+                if constexpr (XCH == 2) {
+                    // the previous pass's CTAs left this tile as [c][t], t = mp + i*M (what the global loads would have read)
+                    const cx<T>* src = tile + c * R + mp;
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) { const cx<T> v = src[i * M]; pre_r[i] = v.x; pre_i[i] = v.y; }
+                } else if ((KIND != KIND_ROW) || (c < rows_valid)) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
                     gload_n<R1>(p, a0, (long long)M * in_rstride, pre_r, pre_i);
                 } else {
@@ -410,11 +425,9 @@ struct PassKernel {
                 uint32_t e = kp0 * (bcol0 + (uint32_t)c);
                 vreg = to_cx<T>(p.tw2.get(e << p.tw_shift));
             }
-            if constexpr (!ASYNC) __syncthreads();
-        }
-        if constexpr (ASYNC) {
-            cp_async_wait_all();
             __syncthreads();
+        } else if constexpr (XCH == 2) {
+            __syncthreads();     // every thread has read its inputs out of the exchanged tile before stage 1 overwrites it
         }
 
         // ---- stage 1: global -> registers -> (twiddle, DFT) -> tile (or global when S == 1) ------
@@ -429,16 +442,7 @@ struct PassKernel {
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
                 T xr[R1], xi[R1];
                 [[maybe_unused]] const bool valid = (KIND != KIND_ROW) || (c < rows_valid);
-                if constexpr (ASYNC) {
-                    const int j0 = rev_tail<RL>(mp);
-                    const bool swap = p.in_interleaved == 2;
-#pragma unroll
-                    for (int i = 0; i < R1; ++i) {
-                        cx<T> v = tile[Addr::at(j0 * R1 + i, c)];
-                        xr[i] = swap ? v.y : v.x;
-                        xi[i] = swap ? v.x : v.y;
-                    }
-                } else if constexpr (PRELOAD) {
+                if constexpr (PRELOAD) {
 #pragma unroll
                     for (int i = 0; i < R1; ++i) { xr[i] = pre_r[i]; xi[i] = pre_i[i]; }
                 } else if (valid) {
@@ -482,7 +486,7 @@ struct PassKernel {
                 }
             }
         };
-        if constexpr (ASYNC || PRELOAD) stage1(std::integral_constant<int, 0>{});
+        if constexpr (PRELOAD) stage1(std::integral_constant<int, 0>{});
         else if (p.in_interleaved == 0) stage1(std::integral_constant<int, 0>{});
         else if (p.in_interleaved == 1) stage1(std::integral_constant<int, 1>{});
         else stage1(std::integral_constant<int, 2>{});
@@ -492,9 +496,26 @@ struct PassKernel {
 
 };
 
-template <typename T, class RL, int C, int NT, int KIND, int ASYNC, int VARIANT = 0, int MINB = 0>
+template <typename T, class RL, int C, int NT, int KIND, int VARIANT = 0, int MINB = 0>
 __global__ void __launch_bounds__(NT, MINB) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {
-    PassKernel<T, RL, C, NT, KIND, ASYNC, VARIANT>::body(p, blockIdx.x);
+    PassKernel<T, RL, C, NT, KIND, 0, VARIANT>::body(p, blockIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One HBM pass for transforms that fit the shared memory of a thread-block cluster (2^13..2^17 points): the K CTAs of a
+// cluster run pass 1 (PK1, KIND_COL, each CTA P2/K adjacent columns of the P1 x P2 view of the signal) out of global
+// memory, exchange the intermediate through distributed shared memory (every CTA scatters its results into the tiles of
+// the CTAs that own those rows in pass 2 -- the transpose that a two-launch plan does through a global workspace), and
+// run pass 2 (PK2, KIND_TRANS, P1/K rows each) out of shared memory into global memory.  HBM sees the signal once in
+// and once out; grid = transforms x K, cluster dimension K (launch attribute).
+// Replaces, for these sizes, the L1-resident leaf of the reference's recursion (algorithms/dit.rs:27-93).
+// ---------------------------------------------------------------------------------------------
+template <class PK1, class PK2, typename T, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) fft_cluster2_kernel(const __grid_constant__ PassParams<T> p1,
+                                                                const __grid_constant__ PassParams<T> p2) {
+    PK1::body(p1, blockIdx.x);      // ends with: cluster barrier, scatter into the cluster's tiles
+    cluster_sync();                 // every CTA's scatter has landed; nobody writes another CTA's tile after this
+    PK2::body(p2, blockIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@
 #include <vector>
 
 #include "../../include/phastft_cuda.h"
-#include "fft_kernels.cuh"
+#include "registry.h"
 
 using namespace phast;
 
@@ -69,245 +69,15 @@ struct DeviceGuard {
 };
 
 // =================================================================================================
-// kernel registry
+// kernel registry (the kernels themselves are instantiated in reg_strided.cu / reg_row.cu / reg_multi.cu)
 // =================================================================================================
-template <typename T>
-struct KernelEntry {
-    int kind, R, C, NT, first_radix, stages, async, variant;
-    size_t smem;
-    const void* fn;
-    std::string radices;
-};
-
-// experimental variants (PHASTFT_VARIANT=<id> selects them; id 0 = the default kernels)
-template <typename T, int KIND, int C, int NT, int VARIANT, int MINB, int ID, int... Rs>
-KernelEntry<T> make_entry_v() {
-    using RL = RadixList<Rs...>;
-    using PK = PassKernel<T, RL, C, NT, KIND, 0, VARIANT>;
-    KernelEntry<T> e;
-    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.async = 0; e.variant = ID;
-    e.smem = PK::SMEM_BYTES;
-    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, 0, VARIANT, MINB>);
-    const int rs[] = {Rs...};
-    for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
-    if (ID) e.radices += ",v" + std::to_string(ID);
-    return e;
-}
-
-template <typename T, int KIND, int C, int NT, int ASYNC, int... Rs>
-KernelEntry<T> make_entry_a() {
-    using RL = RadixList<Rs...>;
-    using PK = PassKernel<T, RL, C, NT, KIND, ASYNC>;
-    static_assert(NT % 32 == 0, "whole warps");
-    static_assert(KIND != KIND_COL || NT % C == 0, "a COL thread keeps its column");
-    static_assert(PK::SMEM_BYTES <= 227 * 1024, "tile exceeds the 227 KB shared memory of an sm_100 CTA");
-    KernelEntry<T> e;
-    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.async = ASYNC; e.variant = 0;
-    e.smem = PK::SMEM_BYTES;
-    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, ASYNC>);
-    const int rs[] = {Rs...};
-    for (int i = 0; i < (int)sizeof...(Rs); ++i) e.radices += (i ? "x" : "") + std::to_string(rs[i]);
-    if (ASYNC) e.radices += ",async";
-    return e;
-}
-template <typename T, int KIND, int C, int NT, int... Rs>
-KernelEntry<T> make_entry() { return make_entry_a<T, KIND, C, NT, 0, Rs...>(); }
-
-// Tile width in columns for the strided (HBM-facing) kinds: C * sizeof(T) = 64 B (CN) or 128 B (CW).
-template <typename T> struct TileC;
-template <> struct TileC<double> { static constexpr int CH = 4, CN = 8, CW = 16; };
-template <> struct TileC<float> { static constexpr int CH = 8, CN = 16, CW = 32; };
-
-// The registry.  Every (kind, R, C) the planner can ask for has a DEFAULT entry (variant id 0) whose
-// code-generation knobs (task-loop unrolling, twiddle derivation, register budget, thread count) are
-// the ones that measured fastest on B200 for that tile (tools/tune*.py, profiles/r01_tuning.md);
-// the other ids are kept selectable (PHASTFT_VARIANT / PHASTFT_PASS_VARIANT) for re-tuning.
-//   knob bits: 1 = unroll the task loops of the shared-memory stages, 2 = stage twiddles from 3 table
-//   loads + products, 4 = unroll the stage-1 task loop;  MINB = CTAs/SM the register budget is sized for.
-template <typename T, int KIND>
-void add_strided_kernels(std::vector<KernelEntry<T>>& v) {
-    constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN, CW = TileC<T>::CW;
-    constexpr bool F64 = sizeof(T) == 8;
-    // ---- defaults -------------------------------------------------------------------------------------
-    v.push_back(make_entry_v<T, KIND, 8 * CN, 64, 0, 0, 0, 16>());          // single-stage R=16 (middle pass of e.g. {8,4,8})
-    v.push_back(make_entry_v<T, KIND, 8 * CN, 64, 0, 0, 0, 8>());
-    v.push_back(make_entry_v<T, KIND, CH, 32, 0, 0, 0, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CH, 64, 0, 0, 0, 16, 8>());
-    v.push_back(make_entry_v<T, KIND, CH, F64 ? 64 : 128, 0, 0, 0, 16, 16>());
-    v.push_back(make_entry_v<T, KIND, CN, 32, 0, 0, 0, 4, 8>());
-    v.push_back(make_entry_v<T, KIND, CW, 64, 0, 0, 0, 4, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 64, 0, 0, 0, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CW, 128, 0, 0, 0, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, 2 * CW, 256, 0, 0, 0, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 0, 16, 8>());
-    v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 8>());
-    v.push_back(make_entry_v<T, KIND, 2 * CW, 256, 0, 0, 0, 16, 8>());
-    // R = 256 as two radix-16 stages (one shared-memory exchange): 5.5 TB/s as a first pass vs 4.25 TB/s for
-    // 4x8x8 (tune9/tune10); 128 threads for the 64-byte-run f64 tile (128 tasks per stage)
-    if constexpr (F64) {
-        v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 0, 16, 16>());
-        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 16>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());      // +20% over the plain build (tune5)
-        v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 32, 32>());       // two radix-32 stages: 19.2-19.5 vs 19.4-20.3 us at 2^20 (tune23/25)
-        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 70, 16, 8, 8>());    // id 70: the three-stage build (512 threads: 20.0 vs 21.2 us, tune8)
-        v.push_back(make_entry_v<T, KIND, CH, 512, 0, 1, 0, 16, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 60, 16, 8, 8>());
-    } else {
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 0, 16, 16>());
-        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 0, 16, 16>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CW, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH, 256, 3, 2, 0, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 0, 16, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 60, 16, 8, 8>());
-        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 0, 0, 32, 32>());       // two radix-32 stages: 14.0 vs 15.3 us at 2^20 (tune25)
-        v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 70, 16, 8, 8>());    // id 70: the three-stage build
-        v.push_back(make_entry_v<T, KIND, CH, 512, 0, 1, 60, 16, 8, 8>());
-    }
-    // ---- alternates kept for re-tuning ------------------------------------------------------------------
-    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 8, 8, 8>());          // id 1: plain build
-    v.push_back(make_entry_v<T, KIND, CN, 256, 2, 3, 2, 8, 8, 8>());          // id 2
-    v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 4, 8, 8, 8>());          // id 4
-    v.push_back(make_entry_v<T, KIND, CN, 512, 0, 2, 5, 8, 8, 8>());          // id 5: 512 threads
-    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 4, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 1, 4, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 256, 2, 3, 2, 4, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 256, 7, 2, 4, 4, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CW, 256, 7, 2, 4, 4, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 1, 16, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CN, 256, 0, 1, 20, 16, 8, 8>());        // id 20: 256 threads
-    v.push_back(make_entry_v<T, KIND, CN, 512, 0, 1, 25, 8, 8, 16>());        // id 25
-    // ids 61-65: 1024-row tiles at half width (64 KB f64 / 32 KB f32), for interleaved intermediates
-    v.push_back(make_entry_v<T, KIND, CH, 256, 4, 1, 61, 16, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CH, 256, 7, 2, 62, 16, 8, 8>());       // register budget pinned to 2 CTAs/SM (150 regs and 1 CTA/SM otherwise)
-    v.push_back(make_entry_v<T, KIND, CH, 256, 7, 3, 67, 16, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CH, 256, 0, 2, 63, 16, 8, 8>());
-    v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 64, 4, 16, 16>());
-    v.push_back(make_entry_v<T, KIND, CH, 256, 0, 1, 65, 16, 16, 4>());
-    v.push_back(make_entry_v<T, KIND, CH, 128, 0, 1, 66, 16, 8, 8>());
-    // (four-stage 64-register builds of this tile -- 8x8x4x4, 4x4x8x8, 8x8x8x2, 2x8x8x8 at 512 threads, 32 warps/SM --
-    //  measured 582-615 us against 508 us for id 62 on the 2^26 middle pass, tools/tune28.py: not kept)
-    // (a persistent double-buffered build of this pass -- one CTA per SM, cp.async prefetch of the next tile under the
-    //  current tile's stages -- and quarter-width 32 KB tiles at 4-6 CTAs/SM were built and measured: 779-818 us and
-    //  669-901 us against 505 us for id 62 on the 2^26 f64 middle pass; see profiles/r01_tuning.md. Removed again.)
-    // id 32: radix-32 register stages -> 1024 and 512 rows with ONE shared-memory exchange
-    if constexpr (F64) {
-        v.push_back(make_entry_v<T, KIND, CH, 128, 0, 0, 32, 32, 32>());      // 168 regs, 64 KB tile: 3 CTAs/SM
-        v.push_back(make_entry_v<T, KIND, CH, 64, 0, 0, 32, 16, 32>());
-        v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 32, 16, 32>());
-        v.push_back(make_entry_v<T, KIND, CW, 256, 0, 0, 32, 16, 32>());
-        v.push_back(make_entry_v<T, KIND, CN, 128, 0, 0, 34, 32, 16>());
-    } else {
-        v.push_back(make_entry_v<T, KIND, CN, 512, 0, 0, 32, 32, 32>());
-        v.push_back(make_entry_v<T, KIND, CH, 128, 0, 0, 32, 16, 32>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 32, 16, 32>());
-        v.push_back(make_entry_v<T, KIND, CW, 512, 0, 0, 32, 16, 32>());
-        v.push_back(make_entry_v<T, KIND, CN, 256, 0, 0, 34, 32, 16>());
-    }
-}
-
 template <typename T>
 const std::vector<KernelEntry<T>>& registry() {
     static const std::vector<KernelEntry<T>> reg = [] {
         std::vector<KernelEntry<T>> v;
-        // ---- whole transform in one CTA (rows contiguous in and out) -------------------------------
-        v.push_back(make_entry<T, KIND_ROW, 64, 64, 2>());
-        v.push_back(make_entry<T, KIND_ROW, 64, 64, 4>());
-        v.push_back(make_entry<T, KIND_ROW, 64, 64, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 32, 32, 16>());
-        v.push_back(make_entry<T, KIND_ROW, 16, 64, 4, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 8, 64, 8, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 4, 64, 16, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 2, 64, 4, 8, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 1, 64, 8, 8, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 1, 128, 16, 8, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 1, 256, 4, 8, 8, 8>());
-        v.push_back(make_entry<T, KIND_ROW, 1, 256, 8, 8, 8, 8>());
-        if constexpr (sizeof(T) == 4) v.push_back(make_entry<T, KIND_ROW, 1, 512, 16, 8, 8, 8>());
-        v.push_back(make_entry_v<T, KIND_ROW, 1, 256, 0, 0, 70, 16, 16, 16>());
-        v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 70, 8, 16, 16>());
-        v.push_back(make_entry_v<T, KIND_ROW, 1, 64, 0, 0, 70, 4, 16, 16>());
-        v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 70, 16, 16>());
-        // ids 80/81: one-CTA kernels for BATCHES of small transforms (tools/tune29.py, 2^24 points per call):
-        // 4..16 points split in two stages so the lanes of a warp run along the row (coalesced) instead of one
-        // row per lane -- n=16 f64 259 -> 121 us; 512 / 1024 points with ONE shared-memory exchange (32x16, 32x32)
-        // -- f32 n=1024 86 -> 52 us; 2048 points as 16x16x8.  The losing candidates (8x8x8 at 2 and 4 rows per CTA,
-        // 16x32, 32x8x8, 2x32x32, 32x16x8, 4x32x32) are not kept.
-        v.push_back(make_entry_v<T, KIND_ROW, 64, 128, 0, 0, 80, 2, 2>());
-        v.push_back(make_entry_v<T, KIND_ROW, 64, 128, 0, 0, 80, 2, 4>());
-        v.push_back(make_entry_v<T, KIND_ROW, 32, 128, 0, 0, 80, 4, 4>());
-        v.push_back(make_entry_v<T, KIND_ROW, 16, 64, 0, 0, 81, 4, 4>());
-        v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 81, 32, 16>());
-        v.push_back(make_entry_v<T, KIND_ROW, 2, 64, 0, 0, 81, 32, 32>());
-        v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 81, 16, 16, 8>());
-
-        // ---- first / middle passes (KIND_COL) and last pass (KIND_TRANS) ---------------------------
-        add_strided_kernels<T, KIND_COL>(v);
-        add_strided_kernels<T, KIND_TRANS>(v);
-        return v;
-    }();
-    return reg;
-}
-
-// ---- fused two-pass launches (fft_fused2_kernel) for the default 2-pass plans of lone transforms ----------
-template <typename T>
-struct FusedEntry {
-    int R1, C1, NT1, R2, C2, NT2;
-    std::string rad1, rad2;
-    const void* fn;
-    int NT;
-    size_t smem;
-};
-template <class RL> std::string radix_string() {
-    std::string r;
-    for (int i = 0; i < RL::S; ++i) r += (i ? "x" : "") + std::to_string(RL::rad(i));
-    return r;
-}
-template <typename T, class RL1, int C1, int NT1, int V1, class RL2, int C2, int NT2, int V2>
-FusedEntry<T> make_fused() {
-    using PK1 = PassKernel<T, RL1, C1, NT1, KIND_COL, 0, V1>;
-    using PK2 = PassKernel<T, RL2, C2, NT2, KIND_TRANS, 0, V2>;
-    constexpr int NTF = NT1 > NT2 ? NT1 : NT2;
-    FusedEntry<T> e;
-    e.R1 = RL1::R(); e.C1 = C1; e.NT1 = NT1; e.R2 = RL2::R(); e.C2 = C2; e.NT2 = NT2;
-    e.rad1 = radix_string<RL1>(); e.rad2 = radix_string<RL2>();
-    e.fn = reinterpret_cast<const void*>(&fft_fused2_kernel<PK1, PK2, T, NTF, 1>);
-    e.NT = NTF;
-    e.smem = PK1::SMEM_BYTES > PK2::SMEM_BYTES ? PK1::SMEM_BYTES : PK2::SMEM_BYTES;
-    return e;
-}
-// The pairs are exactly the default 2-pass plans 2^11..2^20 (tools/tune17.py prints them); the knob
-// values (V) repeat the ones of the default registry entries so fused and unfused results are bit-identical.
-template <typename T>
-const std::vector<FusedEntry<T>>& fused_registry() {
-    static const std::vector<FusedEntry<T>> reg = [] {
-        std::vector<FusedEntry<T>> v;
-        constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN;
-        using R32 = RadixList<4, 8>; using R64 = RadixList<8, 8>; using R128 = RadixList<16, 8>;
-        using R256 = RadixList<16, 16>; using R512 = RadixList<8, 8, 8>; using R1024 = RadixList<16, 8, 8>;
-        if constexpr (sizeof(T) == 8) {
-            v.push_back(make_fused<T, R32, CN, 32, 0, R64, CH, 32, 0>());          // 2^11
-            v.push_back(make_fused<T, R64, CH, 32, 0, R64, CH, 32, 0>());          // 2^12
-            v.push_back(make_fused<T, R64, CH, 32, 0, R128, CH, 64, 0>());         // 2^13
-            v.push_back(make_fused<T, R128, CH, 64, 0, R128, CH, 64, 0>());        // 2^14
-            v.push_back(make_fused<T, R128, CH, 64, 0, R256, CH, 64, 0>());        // 2^15
-            v.push_back(make_fused<T, R256, CH, 64, 0, R256, CH, 64, 0>());        // 2^16
-            v.push_back(make_fused<T, R512, CH, 256, 3, R256, CH, 64, 0>());       // 2^17
-            v.push_back(make_fused<T, R512, CH, 256, 3, R512, CH, 256, 3>());      // 2^18
-            v.push_back(make_fused<T, R1024, CH, 512, 0, R512, CH, 256, 3>());     // 2^19
-            v.push_back(make_fused<T, R1024, CN, 512, 0, R1024, CN, 512, 0>());    // 2^20
-        } else {
-            v.push_back(make_fused<T, R64, CH, 32, 0, R128, CH, 64, 0>());         // 2^13
-            v.push_back(make_fused<T, R128, CH, 64, 0, R128, CH, 64, 0>());        // 2^14
-            v.push_back(make_fused<T, R128, CH, 64, 0, R256, CH, 128, 0>());       // 2^15
-            v.push_back(make_fused<T, R256, CH, 128, 0, R256, CH, 128, 0>());      // 2^16
-            v.push_back(make_fused<T, R512, CH, 256, 3, R256, CH, 128, 0>());      // 2^17
-            v.push_back(make_fused<T, R512, CH, 256, 3, R512, CH, 256, 3>());      // 2^18
-            v.push_back(make_fused<T, R1024, CH, 256, 0, R512, CH, 256, 3>());     // 2^19
-            v.push_back(make_fused<T, R1024, CH, 256, 0, R1024, CH, 256, 0>());    // 2^20
-        }
+        add_row_kernels<T>(v);                       // whole transform in one CTA (rows contiguous in and out)
+        add_strided_kernels<T, KIND_COL>(v);         // first / middle passes
+        add_strided_kernels<T, KIND_TRANS>(v);       // last pass
         return v;
     }();
     return reg;
@@ -357,6 +127,25 @@ void root_of_unity(uint64_t k, uint64_t n, double& re, double& im) {
 // plans
 // =================================================================================================
 constexpr int MAX_PASSES = 3;
+
+// First 256 bytes of a plan's table blob: what the rest of the blob was laid out for.  Offsets and the W_L^(c*m)
+// tables depend on the pass decomposition and on each pass's kernel (tile width, first radix), which can differ
+// between ranks (PlannerMode::Tune, PHASTFT_* overrides): import / broadcast compare headers first.
+constexpr size_t BLOB_HEADER_BYTES = 256;
+struct BlobHeader {
+    uint64_t magic;        // "PHASTFT2"
+    uint64_t bytes;        // whole blob, header included
+    uint64_t n;
+    uint32_t precision_bits, num_passes;
+    uint64_t layout_sig;   // FNV-1a of the plan description (factors, kernels, radices, variants)
+};
+static_assert(sizeof(BlobHeader) <= BLOB_HEADER_BYTES, "header fits its slot");
+constexpr uint64_t BLOB_MAGIC = 0x3254464854534150ull;
+inline uint64_t fnv1a(const std::string& str) {
+    uint64_t h = 1469598103934665603ull;
+    for (unsigned char c : str) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
 constexpr int ALT_ROW_PASS = -1;   // launch_pass(): use Plan::alt_row
 
 template <typename T>
@@ -376,7 +165,12 @@ struct Plan {
     int device = 0;
     int num_passes = 0;
     PassDesc<T> pass[MAX_PASSES];
-    PassDesc<T> alt_row;               // N <= 4096 planned as two passes: the one-CTA kernel, used for batches
+    PassDesc<T> alt_row;               // multi-pass N that one CTA can hold (<= 128 KB): the one-CTA kernel, used for batches
+    size_t alt_row_min_batch = 4;
+    const ClusterEntry<T>* cl = nullptr;   // both passes in ONE launch by a thread-block cluster (exchange through DSMEM)
+    PassDesc<T> cl_pass[2];
+    size_t cl_min_batch = 0;           // calls with at least this many transforms use the cluster launch
+    int cl_max_active = 0;             // cudaOccupancyMaxActiveClusters of that launch on this device
     const FusedEntry<T>* fused = nullptr;   // 2-pass plans: both passes in one cooperative launch (lone transforms)
     int fused_grid = 0;
     unsigned* fuse_bar = nullptr;      // grid barrier state {count, generation}
@@ -566,6 +360,8 @@ const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
         case 512: case 1024: want = 81; break;
         case 2048: want = f64 ? 81 : 70; break;
         case 4096: want = f64 ? 70 : 0; break;
+        case 8192: want = f64 ? 90 : 0; break;
+        case 16384: want = 90; break;
         default: break;
     }
     if (!want) return dflt;
@@ -599,7 +395,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
     // two-level W_N table
     pl->lo_bits = (ln + 1) / 2;
     const size_t n_lo = size_t(1) << pl->lo_bits, n_hi = size_t(1) << (ln - pl->lo_bits);
-    size_t off = 0;
+    size_t off = BLOB_HEADER_BYTES;
     pl->hi_off = off; off += n_hi * sizeof(double2);
     pl->lo_off = off; off += n_lo * sizeof(double2);
 
@@ -648,27 +444,60 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         }
         off = (off + 255) & ~size_t(255);
     }
-    if (pl->num_passes >= 2 && ln <= 12) {
+    // Batches of transforms that one CTA can hold (128 KB tile: 2^13 f64, 2^14 f32) use a one-CTA kernel: one launch,
+    // one HBM round trip.  PHASTFT_ONE_CTA_MAX (log2) lowers the limit for re-tuning.
+    int one_cta_max = sizeof(T) == 8 ? 13 : 14;
+    if (const char* env = getenv("PHASTFT_ONE_CTA_MAX")) one_cta_max = atoi(env);
+    if (pl->num_passes >= 2 && ln <= one_cta_max) {
         PassDesc<T>& d = pl->alt_row;
         d.log2R = ln; d.log2A = 0; d.log2B = 0; d.log2R1 = ln;
         d.k = pick_kernel<T>(KIND_ROW, 1 << ln, 1 << 30, 0, false);
-        if (d.k) d.k = pick_row_batch_kernel<T>(1 << ln, d.k);   // alt_row is only ever used for batches
+        d.k = pick_row_batch_kernel<T>(1 << ln, d.k);            // alt_row is only ever used for batches
         d.kb = d.k;
         if (d.k) {
             d.tw_stage_off = off; off += (size_t(1) << ln) * sizeof(cx<T>);
             off = (off + 255) & ~size_t(255);
+            pl->alt_row_min_batch = ln <= 12 ? 4 : 32;
+        }
+    }
+    // Larger transforms up to the shared memory of a cluster (2^14..2^16 f64, 2^15..2^16 f32): both passes in one
+    // cluster launch.  PHASTFT_CLUSTER=0 disables, PHASTFT_CLUSTER_VARIANT=<id> picks a build, PHASTFT_CLUSTER_MIN_BATCH
+    // sets the smallest call that uses it (a lone transform keeps K SMs busy, the two-launch plan the whole chip).
+    {
+        int want = 0, enabled = 1;
+        if (const char* env = getenv("PHASTFT_CLUSTER")) enabled = atoi(env);
+        if (const char* env = getenv("PHASTFT_CLUSTER_VARIANT")) want = atoi(env);
+        if (enabled && !pl->alt_row.k)
+            for (const auto& ce : cluster_registry<T>())
+                if (ce.log2n == ln && ce.variant == want) { pl->cl = &ce; break; }
+        if (pl->cl) {
+            pl->cl_min_batch = 8;
+            if (const char* env = getenv("PHASTFT_CLUSTER_MIN_BATCH")) pl->cl_min_batch = (size_t)std::max(1, atoi(env));
+            const int l1 = ilog2((size_t)pl->cl->k1.R), l2 = ilog2((size_t)pl->cl->k2.R);
+            PassDesc<T>& a = pl->cl_pass[0];
+            a.k = a.kb = &pl->cl->k1;
+            a.log2R = l1; a.log2A = 0; a.log2B = l2; a.log2R1 = l1;
+            a.tw_stage_off = off; off += (size_t(1) << l1) * sizeof(cx<T>);
+            off = (off + 255) & ~size_t(255);
+            PassDesc<T>& b = pl->cl_pass[1];
+            b.k = b.kb = &pl->cl->k2;
+            b.log2R = l2; b.log2A = l1; b.log2B = 0; b.log2R1 = l1;
+            b.has_tw = 1; b.log2Rprev = l1; b.tw_shift = 0;
+            b.tw_stage_off = off; off += (size_t(1) << l2) * sizeof(cx<T>);
+            b.tw_wc_off = b.tw_wc_off_b = off;
+            off += (size_t)b.k->C * ((size_t(1) << l2) / b.k->first_radix) * sizeof(cx<T>);
+            off = (off + 255) & ~size_t(255);
         }
     }
     // ---- fill the blob ------------------------------------------------------------------------------
-    pl->blob_host.assign(off ? off : 256, 0);
+    pl->blob_host.assign(off, 0);
     {
         double2* hi = reinterpret_cast<double2*>(pl->blob_host.data() + pl->hi_off);
         double2* lo = reinterpret_cast<double2*>(pl->blob_host.data() + pl->lo_off);
         for (size_t h = 0; h < n_hi; ++h) root_of_unity((uint64_t)h << pl->lo_bits, n, hi[h].x, hi[h].y);
         for (size_t l = 0; l < n_lo; ++l) root_of_unity(l, n, lo[l].x, lo[l].y);
     }
-    for (int p = 0; p < pl->num_passes; ++p) {
-        PassDesc<T>& d = pl->pass[p];
+    auto fill_pass_tables = [&](PassDesc<T>& d) {
         const size_t R = size_t(1) << d.log2R;
         cx<T>* tw = reinterpret_cast<cx<T>*>(pl->blob_host.data() + d.tw_stage_off);
         for (size_t e = 0; e < R; ++e) {
@@ -690,16 +519,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                     wc[(size_t)c * M + m].x = (T)re; wc[(size_t)c * M + m].y = (T)im;
                 }
         }
-    }
-    if (pl->alt_row.k) {
-        const size_t R = size_t(1) << pl->alt_row.log2R;
-        cx<T>* tw = reinterpret_cast<cx<T>*>(pl->blob_host.data() + pl->alt_row.tw_stage_off);
-        for (size_t e = 0; e < R; ++e) {
-            double re, im;
-            root_of_unity(e, R, re, im);
-            tw[e].x = (T)re; tw[e].y = (T)im;
-        }
-    }
+    };
+    for (int p = 0; p < pl->num_passes; ++p) fill_pass_tables(pl->pass[p]);
+    if (pl->alt_row.k) fill_pass_tables(pl->alt_row);
+    if (pl->cl) { fill_pass_tables(pl->cl_pass[0]); fill_pass_tables(pl->cl_pass[1]); }
     CUDA_TRY(cudaMalloc(&pl->blob_dev, pl->blob_host.size()));
     CUDA_TRY(cudaMemcpy(pl->blob_dev, pl->blob_host.data(), pl->blob_host.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
@@ -711,6 +534,24 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
     }
     if (pl->alt_row.k)
         CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.k->smem));
+    if (pl->cl) {
+        // usable only if the device can co-schedule at least one cluster of this shape
+        cudaError_t ce = cudaFuncSetAttribute(pl->cl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->cl->smem);
+        if (ce == cudaSuccess && pl->cl->K > 8) ce = cudaFuncSetAttribute(pl->cl->fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        int nclusters = 0;
+        if (ce == cudaSuccess) {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)pl->cl->K); cfg.blockDim = dim3((unsigned)pl->cl->NT); cfg.dynamicSmemBytes = pl->cl->smem;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)pl->cl->K; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            ce = cudaOccupancyMaxActiveClusters(&nclusters, pl->cl->fn, &cfg);
+        }
+        if (ce != cudaSuccess || nclusters < 1) { (void)cudaGetLastError(); pl->cl = nullptr; }
+        pl->cl_max_active = nclusters;
+    }
     if (pl->num_passes >= 2) {
         CUDA_TRY(cudaMalloc(&pl->ws_re, 2 * n * sizeof(T)));
         pl->ws_im = pl->ws_re + n;
@@ -778,7 +619,21 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         if (pl->num_passes >= 2) s += pl->ws_il == 1 ? " [interleaved intermediates]" : pl->ws_il == 0 ? " [planar intermediates]" : "";
         if (pl->fused) s += " [fused launch, grid " + std::to_string(pl->fused_grid) + "]";
         if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
+        if (pl->cl)
+            s += " || batches >= " + std::to_string(pl->cl_min_batch) + ": CLUSTER K=" + std::to_string(pl->cl->K) + " NT=" + std::to_string(pl->cl->NT) +
+                 " " + std::to_string(pl->cl->k1.R) + "(" + pl->cl->k1.radices + ") x " + std::to_string(pl->cl->k2.R) + "(" + pl->cl->k2.radices +
+                 ") smem=" + std::to_string(pl->cl->smem) + (pl->cl->variant ? ",v" + std::to_string(pl->cl->variant) : std::string()) +
+                 " resident clusters=" + std::to_string(pl->cl_max_active);
         pl->description = s;
+    }
+    {
+        BlobHeader h;
+        memset(&h, 0, sizeof(h));
+        h.magic = BLOB_MAGIC; h.bytes = pl->blob_host.size(); h.n = n;
+        h.precision_bits = 8 * sizeof(T); h.num_passes = (uint32_t)pl->num_passes;
+        h.layout_sig = fnv1a(pl->description);
+        memcpy(pl->blob_host.data(), &h, sizeof(h));
+        CUDA_TRY(cudaMemcpy(pl->blob_dev, pl->blob_host.data(), BLOB_HEADER_BYTES, cudaMemcpyHostToDevice));
     }
     *out = pl.release();
     return PHASTFT_OK;
@@ -832,9 +687,19 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
 }
 
 template <typename T>
+int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const PassParams<T>& base, size_t batch, long long k1_lo,
+                          long long k1_cnt, PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out);
+
+template <typename T>
 int32_t prepare_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, long long k1_lo, long long k1_cnt,
                      PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out) {
     const PassDesc<T>& d = (p == ALT_ROW_PASS) ? pl.alt_row : pl.pass[p];
+    return prepare_pass_desc(pl, d, p, base, batch, k1_lo, k1_cnt, prm_out, k_out, blocks_out);
+}
+
+template <typename T>
+int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const PassParams<T>& base, size_t batch, long long k1_lo,
+                          long long k1_cnt, PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out) {
     const bool many = d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
     const KernelEntry<T>* k = many ? d.kb : d.k;
     PassParams<T> prm = base;
@@ -880,6 +745,32 @@ inline size_t l2_chunk_bytes() {
     return v;
 }
 
+// caller holds pl.mu
+template <typename T>
+int32_t grow_workspace(const Plan<T>& pl, size_t transforms, cudaStream_t stream) {
+    if (pl.ws_elems >= transforms * pl.n) return PHASTFT_OK;
+    if (stream) CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (pl.ws_re) cudaFree(pl.ws_re);
+    pl.ws_re = pl.ws_im = nullptr; pl.ws_elems = 0;
+    CUDA_TRY(cudaMalloc(&pl.ws_re, 2 * transforms * pl.n * sizeof(T)));
+    pl.ws_im = pl.ws_re + transforms * pl.n;
+    pl.ws_elems = transforms * pl.n;
+    return PHASTFT_OK;
+}
+
+template <typename T>
+int32_t plan_reserve(const Plan<T>* pl, size_t batch) {
+    if (!pl) return fail(PHASTFT_ERR_INVALID_ARG, "plan == NULL");
+    if (pl->num_passes < 2 || batch <= 1) return PHASTFT_OK;       // one-CTA plans have no workspace
+    DeviceGuard g(pl->device);
+    std::lock_guard<std::mutex> lock(pl->mu);
+    const size_t bytes_per = pl->n * 2 * sizeof(T);
+    size_t chunk = std::max<size_t>(1, l2_chunk_bytes() / bytes_per);
+    chunk = std::min(chunk, batch);
+    return grow_workspace(*pl, chunk, nullptr);
+}
+
 // `pass_events` (profiling aid, bench.py roofline): if non-NULL, num_passes+1 events are recorded
 // around the passes of the FIRST chunk.
 template <typename T>
@@ -894,7 +785,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
             return fail(PHASTFT_ERR_INVALID_ARG, "N == 1 supports only the in-place unscaled form");
         return PHASTFT_OK;
     }
-    const bool use_alt_row = pl.alt_row.k != nullptr && batch >= 4;
+    const bool use_alt_row = pl.alt_row.k != nullptr && batch >= pl.alt_row_min_batch;
     if (pl.num_passes == 1 || use_alt_row) {
         const int which = use_alt_row ? ALT_ROW_PASS : 0;
         size_t done = 0;
@@ -919,21 +810,51 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
         }
         return PHASTFT_OK;
     }
+    // ---- both passes in one cluster launch: no workspace, HBM sees the batch once in and once out ----------------
+    if (pl.cl && batch >= pl.cl_min_batch) {
+        const size_t max_chunk = (size_t(1) << 30) / (size_t)pl.cl->K;        // grid = transforms x K CTAs
+        for (size_t done = 0; done < batch; done += max_chunk) {
+            const size_t nb = std::min(batch - done, max_chunk);
+            PassParams<T> b1, b2, p1, p2;
+            memset(&b1, 0, sizeof(b1)); memset(&b2, 0, sizeof(b2));
+            b1.scale = T(1);
+            b1.in_re = io.in_re + (io.in_il ? 2 : 1) * done * io.in_bstride;
+            b1.in_im = io.in_im ? io.in_im + done * io.in_bstride : nullptr;
+            b1.in_bstride = io.in_bstride; b1.in_interleaved = io.in_il;
+            b1.xch_log2P2 = pl.cl_pass[1].log2R;
+            b1.xch_log2CB = ilog2((size_t)pl.cl->k2.C);
+            b2.out_re = io.out_re + (io.out_il ? 2 : 1) * done * io.out_bstride;
+            b2.out_im = io.out_im ? io.out_im + done * io.out_bstride : nullptr;
+            b2.out_bstride = io.out_bstride; b2.out_interleaved = io.out_il;
+            b2.scale = scale;
+            const KernelEntry<T>* k1 = nullptr; const KernelEntry<T>* k2 = nullptr;
+            unsigned long long t1 = 0, t2 = 0;
+            int32_t st = prepare_pass_desc(pl, pl.cl_pass[0], 0, b1, nb, 0, -1, p1, k1, t1);
+            if (!st) st = prepare_pass_desc(pl, pl.cl_pass[1], 1, b2, nb, 0, -1, p2, k2, t2);
+            if (st) return st;
+            if (t1 != t2 || t1 != (unsigned long long)nb * pl.cl->K) return fail(PHASTFT_ERR_INVALID_ARG, "cluster plan: tile count mismatch");
+            void* args[] = {&p1, &p2};
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)t1); cfg.blockDim = dim3((unsigned)pl.cl->NT); cfg.dynamicSmemBytes = pl.cl->smem; cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)pl.cl->K; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
+            CUDA_TRY(cudaLaunchKernelExC(&cfg, pl.cl->fn, args));
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (pass_events && done == 0)
+                for (int q = 1; q <= pl.num_passes; ++q) CUDA_TRY(cudaEventRecord(pass_events[q], stream));
+        }
+        return PHASTFT_OK;
+    }
     // multi-pass: in -> ws (COL) [-> ws (COL)] -> out (TRANS), batch processed in L2-sized chunks
     std::lock_guard<std::mutex> lock(pl.mu);
     const size_t bytes_per = pl.n * 2 * sizeof(T);
     size_t chunk = std::max<size_t>(1, l2_chunk_bytes() / bytes_per);
     chunk = std::min(chunk, batch);
     if (pl.num_passes == 3 && pl.ws2_re != nullptr) chunk = 1;
-    if (pl.ws_elems < chunk * pl.n) {
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        CUDA_TRY(cudaDeviceSynchronize());
-        if (pl.ws_re) cudaFree(pl.ws_re);
-        pl.ws_re = pl.ws_im = nullptr; pl.ws_elems = 0;
-        CUDA_TRY(cudaMalloc(&pl.ws_re, 2 * chunk * pl.n * sizeof(T)));
-        pl.ws_im = pl.ws_re + chunk * pl.n;
-        pl.ws_elems = chunk * pl.n;
-    }
     // Workspace reuse is ordered by the stream itself when consecutive calls use the same stream;
     // a call on a different stream first waits for the previous user.  While `stream` is being
     // captured into a CUDA graph the cross-stream bookkeeping is skipped (the graph's owner orders
@@ -941,6 +862,15 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
     const bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (pl.ws_elems < chunk * pl.n) {
+        // The plan is created with room for one transform; the first batched call grows it (synchronising).
+        // phastft_plan_dit_*_reserve(batch) does this ahead of time; inside a graph capture growing is an error.
+        if (capturing)
+            return fail(PHASTFT_ERR_INVALID_ARG, "the plan's workspace is too small for this batch and the stream is being captured: "
+                                                 "call phastft_plan_dit_*_reserve(batch) before capturing");
+        int32_t st = grow_workspace(pl, chunk, stream);
+        if (st) return st;
+    }
     if (!capturing && pl.ws_last_stream != stream && pl.ws_used) CUDA_TRY(cudaStreamWaitEvent(stream, pl.ws_free, 0));
     const int P = pl.num_passes;
     if (P == 2 && pl.fused && batch == 1 && !pass_events) {
@@ -1219,9 +1149,11 @@ template <typename T>
 int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, size_t batch, size_t bstride, int direction) {
     if (!plans || num_plans <= 0 || !re || !im) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
     if (direction != PHASTFT_FORWARD && direction != PHASTFT_REVERSE) return fail(PHASTFT_ERR_INVALID_ARG, "direction must be 1 or -1");
+    for (int g = 0; g < num_plans; ++g)
+        if (!plans[g]) return fail(PHASTFT_ERR_INVALID_ARG, "NULL plan in the plan list");
     const size_t n = plans[0]->n;
     for (int g = 0; g < num_plans; ++g)
-        if (!plans[g] || plans[g]->n != n) return fail(PHASTFT_ERR_PLAN_MISMATCH);
+        if (plans[g]->n != n) return fail(PHASTFT_ERR_PLAN_MISMATCH);
     if (bstride < n) return fail(PHASTFT_ERR_INVALID_ARG, "batch_stride < N");
     if (batch == 0) return PHASTFT_OK;
     std::vector<std::mutex*> locks;
@@ -1246,7 +1178,8 @@ int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, s
         for (auto& s : sh)
             if (s.ev) {
                 DeviceGuard guard(s.pl->device);
-                for (int k = 0; k < NSLOT; ++k) { cudaEventDestroy(s.h2d_done[k]); cudaEventDestroy(s.fft_done[k]); cudaEventDestroy(s.d2h_done[k]); }
+                for (int k = 0; k < NSLOT; ++k)
+                    for (cudaEvent_t e : {s.h2d_done[k], s.fft_done[k], s.d2h_done[k]}) if (e) cudaEventDestroy(e);
                 s.ev = false;
             }
     };
@@ -1271,12 +1204,15 @@ int32_t batch_sharded_host(Plan<T>* const* plans, int num_plans, T* re, T* im, s
                     cudaStreamCreateWithFlags(&s.pl->stream_d2h, cudaStreamNonBlocking) != cudaSuccess) { cleanup(); return fail(PHASTFT_ERR_CUDA, "stream create"); }
             }
         }
+        bool ev_ok = true;
+        for (int k = 0; k < NSLOT; ++k) { s.h2d_done[k] = s.fft_done[k] = s.d2h_done[k] = nullptr; }
         for (int k = 0; k < NSLOT; ++k) {
-            cudaEventCreateWithFlags(&s.h2d_done[k], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&s.fft_done[k], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&s.d2h_done[k], cudaEventDisableTiming);
+            ev_ok &= cudaEventCreateWithFlags(&s.h2d_done[k], cudaEventDisableTiming) == cudaSuccess;
+            ev_ok &= cudaEventCreateWithFlags(&s.fft_done[k], cudaEventDisableTiming) == cudaSuccess;
+            ev_ok &= cudaEventCreateWithFlags(&s.d2h_done[k], cudaEventDisableTiming) == cudaSuccess;
         }
         s.ev = true;
+        if (!ev_ok) { (void)cudaGetLastError(); cleanup(); return fail(PHASTFT_ERR_CUDA, "cudaEventCreate"); }
     }
     // issue chunk j of every device before chunk j+1 of any, so all devices stream concurrently
     int32_t st = PHASTFT_OK;
@@ -1401,15 +1337,36 @@ int32_t tables_export(const Plan<T>* pl, void* dst, cudaStream_t s) {
     CUDA_TRY(cudaMemcpyAsync(dst, pl->blob_dev, pl->blob_host.size(), cudaMemcpyDeviceToDevice, s));
     return PHASTFT_OK;
 }
+// Compares a blob header (already on the host) with the plan's own.
+template <typename T>
+int32_t check_blob_header(const Plan<T>* pl, const BlobHeader& h) {
+    BlobHeader mine;
+    memcpy(&mine, pl->blob_host.data(), sizeof(mine));
+    if (h.magic != BLOB_MAGIC) return fail(PHASTFT_ERR_PLAN_MISMATCH, "table blob: bad magic (not a phastft table blob)");
+    if (h.n != mine.n || h.precision_bits != mine.precision_bits) return fail(PHASTFT_ERR_PLAN_MISMATCH, "table blob is for another size / precision");
+    if (h.bytes != mine.bytes || h.num_passes != mine.num_passes || h.layout_sig != mine.layout_sig)
+        return fail(PHASTFT_ERR_PLAN_MISMATCH, "table blob was laid out for a different pass decomposition / kernel choice "
+                                               "(PlannerMode::Tune or a PHASTFT_* override on one rank only?)");
+    return PHASTFT_OK;
+}
+
 template <typename T>
 int32_t tables_import(Plan<T>* pl, const void* src, cudaStream_t s) {
     if (!pl || !src) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
     DeviceGuard g(pl->device);
+    BlobHeader h;
+    CUDA_TRY(cudaMemcpyAsync(&h, src, sizeof(h), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    int32_t st = check_blob_header(pl, h);
+    if (st) return st;
     CUDA_TRY(cudaMemcpyAsync(pl->blob_dev, src, pl->blob_host.size(), cudaMemcpyDeviceToDevice, s));
     return PHASTFT_OK;
 }
 
 typedef int (*nccl_bcast_fn)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+// Two collectives, both joined by every rank whatever it finds (so a mismatching rank cannot leave the others hanging):
+// the root's 256-byte header first, then the root's blob at the size the header states -- into the plan's tables when the
+// layouts agree, into a throw-away buffer (and PHASTFT_ERR_PLAN_MISMATCH) when they do not.
 template <typename T>
 int32_t tables_broadcast(Plan<T>* pl, void* comm, int root, cudaStream_t s) {
     if (!pl || !comm) return fail(PHASTFT_ERR_INVALID_ARG, "NULL argument");
@@ -1420,7 +1377,27 @@ int32_t tables_broadcast(Plan<T>* pl, void* comm, int root, cudaStream_t s) {
     }();
     if (!bcast) return fail(PHASTFT_ERR_NCCL, "libnccl.so.2 / ncclBroadcast not found");
     DeviceGuard g(pl->device);
-    int rc = bcast(pl->blob_dev, pl->blob_dev, pl->blob_host.size(), /*ncclChar*/ 0, root, comm, s);
+    unsigned char* d_hdr = nullptr;
+    CUDA_TRY(cudaMalloc(&d_hdr, BLOB_HEADER_BYTES));
+    int rc = bcast(pl->blob_dev, d_hdr, BLOB_HEADER_BYTES, /*ncclChar*/ 0, root, comm, s);
+    BlobHeader h;
+    memset(&h, 0, sizeof(h));
+    cudaError_t ce = rc == 0 ? cudaMemcpyAsync(&h, d_hdr, sizeof(h), cudaMemcpyDeviceToHost, s) : cudaSuccess;
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+    cudaFree(d_hdr);
+    if (rc != 0) return fail(PHASTFT_ERR_NCCL, "ncclBroadcast (header) returned " + std::to_string(rc));
+    if (ce != cudaSuccess) return fail(PHASTFT_ERR_CUDA, cudaGetErrorString(ce));
+    const int32_t st = check_blob_header(pl, h);
+    if (h.magic != BLOB_MAGIC || h.bytes == 0 || h.bytes > (uint64_t(1) << 34)) return st ? st : fail(PHASTFT_ERR_PLAN_MISMATCH, "bad header from root");
+    unsigned char* target = pl->blob_dev;
+    unsigned char* scratch = nullptr;
+    if (st) {   // join the second collective anyway, at the root's size
+        if (cudaMalloc(&scratch, h.bytes) != cudaSuccess) { (void)cudaGetLastError(); return st; }
+        target = scratch;
+    }
+    rc = bcast(pl->blob_dev, target, h.bytes, /*ncclChar*/ 0, root, comm, s);
+    if (scratch) { cudaStreamSynchronize(s); cudaFree(scratch); }
+    if (st) { const std::string keep = g_last_error; (void)keep; return check_blob_header(pl, h); }
     if (rc != 0) return fail(PHASTFT_ERR_NCCL, "ncclBroadcast returned " + std::to_string(rc));
     return PHASTFT_OK;
 }
@@ -1443,8 +1420,12 @@ struct PlanR2c {
     mutable T* d_spec_im = nullptr;
     mutable T* d_scr_re = nullptr;     // N/2 (c2r scratch when the caller passes none)
     mutable T* d_scr_im = nullptr;
+    mutable cudaEvent_t scr_free = nullptr;        // orders reuse of the plan-owned scratch across streams (like Plan::ws_free)
+    mutable cudaStream_t scr_last_stream = nullptr;
+    mutable bool scr_used = false;
     ~PlanR2c() {
         DeviceGuard g(device);
+        if (scr_free) cudaEventDestroy(scr_free);
         for (void* p : {(void*)tw_dev, (void*)d_real, (void*)d_spec_re, (void*)d_spec_im, (void*)d_scr_re, (void*)d_scr_im})
             if (p) cudaFree(p);
         delete inner;
@@ -1474,6 +1455,7 @@ int32_t build_plan_r2c(size_t n, int device, PlanR2c<T>** out) {
     // c2r scratch for the allocating variants lives in the plan (r2c.rs:716-718 allocates per call)
     CUDA_TRY(cudaMalloc(&pl->d_scr_re, (n / 2) * sizeof(T)));
     CUDA_TRY(cudaMalloc(&pl->d_scr_im, (n / 2) * sizeof(T)));
+    CUDA_TRY(cudaEventCreateWithFlags(&pl->scr_free, cudaEventDisableTiming));
     *out = pl.release();
     return PHASTFT_OK;
 }
@@ -1520,7 +1502,18 @@ int32_t c2r_dev(const PlanR2c<T>* pl, const T* d_ire, const T* d_iim, T* d_out, 
     DeviceGuard g(pl->device);
     const size_t half = pl->n / 2;
     std::unique_lock<std::mutex> lock(pl->mu, std::defer_lock);
-    if (!d_sre) { lock.lock(); d_sre = pl->d_scr_re; d_sim = pl->d_scr_im; }
+    bool own_scratch = false, capturing = false;
+    if (!d_sre) {
+        // The plan-owned scratch is used by kernels that run after this call returns: a caller on another stream
+        // first waits for the previous user (the same protocol as the c2c workspace, run_c2c).
+        lock.lock();
+        d_sre = pl->d_scr_re; d_sim = pl->d_scr_im;
+        own_scratch = true;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
+        capturing = cap != cudaStreamCaptureStatusNone;
+        if (!capturing && pl->scr_used && pl->scr_last_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, pl->scr_free, 0));
+    }
     // (1) pre-process into scratch (r2c.rs:764-780)
     RealParams<T> rp;
     memset(&rp, 0, sizeof(rp));
@@ -1534,7 +1527,13 @@ int32_t c2r_dev(const PlanR2c<T>* pl, const T* d_ire, const T* d_iim, T* d_out, 
     Io<T> io;
     io.in_re = d_sim; io.in_im = d_sre; io.in_il = 0; io.in_bstride = (long long)half;
     io.out_re = d_out; io.out_im = nullptr; io.out_il = 2; io.out_bstride = (long long)half;
-    return run_c2c(*pl->inner, io, 1, T(1) / (T)half, stream);
+    int32_t st = run_c2c(*pl->inner, io, 1, T(1) / (T)half, stream);
+    if (st == PHASTFT_OK && own_scratch && !capturing) {
+        CUDA_TRY(cudaEventRecord(pl->scr_free, stream));
+        pl->scr_last_stream = stream;
+        pl->scr_used = true;
+    }
+    return st;
 }
 
 template <typename T>
@@ -1689,6 +1688,9 @@ void phastft_options_guess(size_t input_size, phastft_options* out) {
     size_t phastft_plan_dit_##SFX##_size(const phastft_plan_dit_##SFX* p) { return p ? AS_CPLAN(T, p)->n : 0; }         \
     const char* phastft_plan_dit_##SFX##_describe(const phastft_plan_dit_##SFX* p) {                                    \
         return p ? AS_CPLAN(T, p)->description.c_str() : "";                                                            \
+    }                                                                                                                   \
+    int32_t phastft_plan_dit_##SFX##_reserve(const phastft_plan_dit_##SFX* p, size_t batch) {                           \
+        return plan_reserve<T>(AS_CPLAN(T, p), batch);                                                                  \
     }                                                                                                                   \
     size_t phastft_plan_dit_##SFX##_tables_bytes(const phastft_plan_dit_##SFX* p) {                                     \
         return p ? AS_CPLAN(T, p)->blob_host.size() : 0;                                                                \

@@ -1,0 +1,78 @@
+// registry.h -- the table of compiled kernels the planner chooses from.
+//
+// The kernels are instantiated in several translation units so the library builds in parallel
+// (__graft_entry__.build()): reg_strided.cu (COL / TRANS passes, compiled once per precision and kind),
+// reg_row.cu (whole-transform-in-one-CTA kernels), reg_multi.cu (cluster and fused two-pass launches).
+// phastft_cuda.cu holds the planner, the launcher and the C ABI and only sees these descriptors.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "fft_kernels.cuh"
+
+namespace phast {
+
+template <typename T>
+struct KernelEntry {
+    int kind, R, C, NT, first_radix, stages, variant;
+    size_t smem;
+    const void* fn;        // fft_pass_kernel<...>; NULL for the passes of a cluster launch (they only exist inside it)
+    std::string radices;
+};
+
+// Both passes of a 2-pass plan in ONE launch by a K-CTA thread-block cluster, intermediate exchanged through
+// distributed shared memory (fft_cluster2_kernel).
+template <typename T>
+struct ClusterEntry {
+    int log2n, K, NT, minb, variant;
+    KernelEntry<T> k1, k2;    // descriptors of the two pass bodies (kind, R, C, first radix) for the planner's tables
+    const void* fn;
+    size_t smem;
+};
+
+// Both passes of a 2-pass plan of a lone L2-resident transform in one launch with a grid barrier (fft_fused2_kernel).
+template <typename T>
+struct FusedEntry {
+    int R1, C1, NT1, R2, C2, NT2;
+    std::string rad1, rad2;
+    const void* fn;
+    int NT;
+    size_t smem;
+};
+
+// Tile width in columns for the strided (HBM-facing) kinds: C * sizeof(T) = 32 B (CH), 64 B (CN) or 128 B (CW).
+template <typename T> struct TileC;
+template <> struct TileC<double> { static constexpr int CH = 4, CN = 8, CW = 16; };
+template <> struct TileC<float> { static constexpr int CH = 8, CN = 16, CW = 32; };
+
+template <class RL> std::string radix_string() {
+    std::string r;
+    for (int i = 0; i < RL::S; ++i) r += (i ? "x" : "") + std::to_string(RL::rad(i));
+    return r;
+}
+
+template <typename T, int KIND, int C, int NT, int VARIANT, int MINB, int ID, int... Rs>
+KernelEntry<T> make_entry_v() {
+    using RL = RadixList<Rs...>;
+    using PK = PassKernel<T, RL, C, NT, KIND, 0, VARIANT>;
+    static_assert(NT % 32 == 0, "whole warps");
+    static_assert(KIND != KIND_COL || NT % C == 0, "a COL thread keeps its column");
+    static_assert(PK::SMEM_BYTES <= 227 * 1024, "tile exceeds the 227 KB shared memory of an sm_100 CTA");
+    KernelEntry<T> e;
+    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.variant = ID;
+    e.smem = PK::SMEM_BYTES;
+    e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, VARIANT, MINB>);
+    e.radices = radix_string<RL>();
+    if (ID) e.radices += ",v" + std::to_string(ID);
+    return e;
+}
+template <typename T, int KIND, int C, int NT, int... Rs>
+KernelEntry<T> make_entry() { return make_entry_v<T, KIND, C, NT, 0, 0, 0, Rs...>(); }
+
+// defined in the reg_*.cu translation units
+template <typename T> void add_row_kernels(std::vector<KernelEntry<T>>& v);
+template <typename T, int KIND> void add_strided_kernels(std::vector<KernelEntry<T>>& v);
+template <typename T> const std::vector<FusedEntry<T>>& fused_registry();
+template <typename T> const std::vector<ClusterEntry<T>>& cluster_registry();
+
+}  // namespace phast

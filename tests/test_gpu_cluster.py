@@ -1,0 +1,156 @@
+"""GPU parity tests for the single-HBM-pass kernels of round 2, all through the C ABI:
+
+* the thread-block-cluster launch (both passes of a two-pass plan in one kernel, intermediate exchanged through
+  distributed shared memory; phastft_b200/csrc/fft_kernels.cuh fft_cluster2_kernel), sizes 2^14..2^16 f64 and 2^15..2^16 f32;
+* the one-CTA kernels for the largest transforms a CTA's shared memory holds (2^13 f64, 2^14 f32).
+
+Checker: the CPU oracle on the same seeded inputs; tolerance as everywhere (tests/test_gpu_c2c.py):
+relative L-infinity <= 4 * eps * log2(N).  Reference path replaced: the L1-resident leaf of the recursion,
+/root/reference/src/algorithms/dit.rs:27-93 (cited, not read at run time).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+C_TOL = 4.0
+
+
+def _pf():
+    import phastft_b200 as pf
+    return pf
+
+
+def _O():
+    from oracle import oracle as O
+    return O
+
+
+def tol(dt, n):
+    return C_TOL * np.finfo(dt).eps * np.log2(n)
+
+
+def rel_linf(a_re, a_im, b_re, b_im):
+    a = np.asarray(a_re, np.float64) + 1j * np.asarray(a_im, np.float64)
+    b = np.asarray(b_re, np.float64) + 1j * np.asarray(b_im, np.float64)
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def planner_cls(dt):
+    pf = _pf()
+    return pf.PlannerDit64 if dt == np.float64 else pf.PlannerDit32
+
+
+SIZES = [(np.float64, 13), (np.float64, 14), (np.float64, 15), (np.float64, 16),
+         (np.float32, 14), (np.float32, 15), (np.float32, 16)]
+
+
+@pytest.mark.parametrize("dt,log_n", SIZES)
+@pytest.mark.parametrize("direction", ["Forward", "Reverse"])
+def test_batched_single_pass_vs_oracle(dt, log_n, direction):
+    """A batch large enough to take the cluster / one-CTA path: every 7th member against the oracle, all members against
+    the lone-transform path (another radix split, so tolerance not bit equality), padding between members untouched."""
+    import torch
+    pf, O = _pf(), _O()
+    n, batch = 1 << log_n, 41
+    stride = n + 24
+    rng = np.random.default_rng(100 * log_n + batch)
+    re_h = rng.uniform(-1, 1, batch * stride).astype(dt)
+    im_h = rng.uniform(-1, 1, batch * stride).astype(dt)
+    planner = planner_cls(dt)(n, 0)
+    desc = planner.describe()
+    assert ("CLUSTER" in desc) or ("batches: ROW" in desc), desc
+    d = getattr(pf.Direction, direction)
+    d_re = torch.from_numpy(re_h).cuda(); d_im = torch.from_numpy(im_h).cuda()
+    before = pf.launch_count()
+    pf.fft_dit_batch(d_re, d_im, d, planner, batch, stride)
+    assert pf.launch_count() - before == 1, "the batch must be ONE launch (one HBM pass)"
+    g_re = d_re.cpu().numpy(); g_im = d_im.cpu().numpy()
+    fft = pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
+    for b in range(batch):
+        s = slice(b * stride, b * stride + n)
+        a, c = re_h[s].copy(), im_h[s].copy()
+        fft(a, c, d, planner)                                   # lone transform: the two-launch plan
+        assert rel_linf(g_re[s], g_im[s], a, c) <= tol(dt, n), (log_n, b)
+        pad = slice(b * stride + n, (b + 1) * stride)
+        assert np.array_equal(g_re[pad], re_h[pad]) and np.array_equal(g_im[pad], im_h[pad])
+        if b % 7 == 0:
+            o_re, o_im = re_h[s].copy(), im_h[s].copy()
+            O.fft_dit(o_re, o_im, O.FORWARD if direction == "Forward" else O.REVERSE)
+            assert rel_linf(g_re[s], g_im[s], o_re, o_im) <= tol(dt, n), (log_n, b)
+
+
+@pytest.mark.parametrize("dt,log_n", [(np.float64, 14), (np.float64, 15), (np.float64, 16), (np.float32, 15), (np.float32, 16)])
+def test_lone_transform_through_the_cluster_launch(dt, log_n, monkeypatch):
+    """PHASTFT_CLUSTER_MIN_BATCH=1 sends even a single host-slice call through the cluster kernel: known answers
+    (impulse -> all ones, lib.rs:171-178), oracle parity, forward->reverse round trip (lib.rs:380-425)."""
+    pf, O = _pf(), _O()
+    monkeypatch.setenv("PHASTFT_CLUSTER_MIN_BATCH", "1")
+    n = 1 << log_n
+    planner = planner_cls(dt)(n, 0)
+    assert "CLUSTER" in planner.describe()
+    fft = pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
+    re = np.zeros(n, dt); im = np.zeros(n, dt); re[0] = 1
+    before = pf.launch_count()
+    fft(re, im, pf.Direction.Forward, planner)
+    assert pf.launch_count() - before == 1
+    assert np.array_equal(re, np.ones(n, dt)) and np.array_equal(im, np.zeros(n, dt))
+    rng = np.random.default_rng(log_n)
+    re = rng.uniform(-1, 1, n).astype(dt); im = rng.uniform(-1, 1, n).astype(dt)
+    re0, im0 = re.copy(), im.copy()
+    o_re, o_im = re.copy(), im.copy()
+    O.fft_dit(o_re, o_im, O.FORWARD)
+    fft(re, im, pf.Direction.Forward, planner)
+    assert rel_linf(re, im, o_re, o_im) <= tol(dt, n)
+    fft(re, im, pf.Direction.Reverse, planner)
+    assert max(np.max(np.abs(re - re0)), np.max(np.abs(im - im0))) <= (1e-10 if dt == np.float64 else 2e-6)
+
+
+@pytest.mark.parametrize("dt,cdt,log_n", [(np.float64, np.complex128, 15), (np.float32, np.complex64, 16)])
+def test_interleaved_and_real_transforms_through_the_cluster_launch(dt, cdt, log_n, monkeypatch):
+    """The interleaved Complex<T> API (lib.rs:41-140) and r2c / c2r (r2c.rs:521-799) feed the same kernel other global
+    layouts on its first load and last store."""
+    pf = _pf()
+    monkeypatch.setenv("PHASTFT_CLUSTER_MIN_BATCH", "1")
+    n = 1 << log_n
+    rng = np.random.default_rng(7 * log_n)
+    re = rng.uniform(-1, 1, n).astype(dt); im = rng.uniform(-1, 1, n).astype(dt)
+    planner = planner_cls(dt)(n, 0)
+    sig = (re + 1j * im).astype(cdt)
+    (pf.fft_64_interleaved_with_planner if dt == np.float64 else pf.fft_32_interleaved_with_planner)(sig, pf.Direction.Forward, planner)
+    a, b = re.copy(), im.copy()
+    (pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner)(a, b, pf.Direction.Forward, planner)
+    assert np.array_equal(sig.real, a) and np.array_equal(sig.imag, b)
+    # real transform of 2n points: the inner half-length c2c has n points
+    x = rng.uniform(-1, 1, 2 * n).astype(dt)
+    rp = (pf.PlannerR2c64 if dt == np.float64 else pf.PlannerR2c32)(2 * n, 0)
+    ore = np.zeros(n + 1, dt); oim = np.zeros(n + 1, dt)
+    (pf.r2c_fft_f64_with_planner if dt == np.float64 else pf.r2c_fft_f32_with_planner)(x, ore, oim, rp)
+    truth = np.fft.rfft(x.astype(np.float64))
+    err = np.max(np.abs((ore + 1j * oim) - truth)) / np.max(np.abs(truth))
+    assert err <= tol(dt, 2 * n) * 2
+    y = np.zeros(2 * n, dt)
+    (pf.c2r_fft_f64_with_planner if dt == np.float64 else pf.c2r_fft_f32_with_planner)(ore, oim, y, rp)
+    assert np.max(np.abs(y - x)) <= (1e-10 if dt == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("dt,log_n,variant", [(np.float32, 16, 1), (np.float32, 16, 100), (np.float32, 15, 100),
+                                              (np.float64, 14, 100), (np.float64, 15, 100), (np.float64, 16, 100)])
+def test_cluster_variants_agree(dt, log_n, variant, monkeypatch):
+    """The alternative cluster shapes (128 KB tiles, other register budgets) compute the same transform."""
+    import torch
+    pf, O = _pf(), _O()
+    monkeypatch.setenv("PHASTFT_CLUSTER_VARIANT", str(variant))
+    n, batch = 1 << log_n, 19
+    planner = planner_cls(dt)(n, 0)
+    assert f",v{variant}" in planner.describe(), planner.describe()
+    rng = np.random.default_rng(variant + log_n)
+    re_h = rng.uniform(-1, 1, batch * n).astype(dt); im_h = rng.uniform(-1, 1, batch * n).astype(dt)
+    d_re = torch.from_numpy(re_h).cuda(); d_im = torch.from_numpy(im_h).cuda()
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, planner, batch)
+    g_re = d_re.cpu().numpy(); g_im = d_im.cpu().numpy()
+    for b in (0, 9, batch - 1):
+        s = slice(b * n, (b + 1) * n)
+        o_re, o_im = re_h[s].copy(), im_h[s].copy()
+        O.fft_dit(o_re, o_im, O.FORWARD)
+        assert rel_linf(g_re[s], g_im[s], o_re, o_im) <= tol(dt, n)
