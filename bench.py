@@ -13,9 +13,10 @@ reads its input from HBM.  With N GPUs every rank transforms its own stream of s
 the only collective is the init-time broadcast of the planner tables): weak scaling, and
 `value` is the whole-job aggregate = N * 2^20 * K / max-over-ranks time.
 
-`--workload batch_f32` measures BASELINE.json's configs[3] instead (4096 x 2^16 f32 forward,
-batch sharded over the ranks, strong scaling); `--workload c2c_f64_2p26` and `r2c_f64_2p24`
-measure configs[2] and configs[4] on one GPU.
+The same JSON line carries, as `batched`, BASELINE.json's configs[3] (4096 x 2^16 f32 forward, batch
+sharded over the N ranks: strong scaling, with a cross-rank bit-exactness check of the shards), so the driver's
+1/2/4/8-GPU runs record the curve the north star names.  `--workload batch_f32` measures only that;
+`--workload c2c_f64_2p26` and `r2c_f64_2p24` measure configs[2] and configs[4] on one GPU.
 
 Only this file's cpu_baseline / --impl reference legs touch oracle/ (the CPU restatement of the
 reference): there it is the thing timed as the CPU baseline, never part of our arm.
@@ -239,7 +240,55 @@ def workload_config(workload: str, gpus: int):
 
 
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def traffic_table():
+    """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu captures)."""
+    for name in ("r02_traffic.json", "traffic.json"):
+        f = ROOT / "profiles" / name
+        if f.exists():
+            try:
+                return json.loads(f.read_text()), name
+            except Exception:
+                pass
+    return {}, None
+
+
+def roofline_block(wl, alg_bytes, ms_per_step, pass_ms_alone, hbm_peak, peak_src, plan_desc, units_note):
+    """achieved = algorithmic bytes of the WHOLE transform (each planar array read once and written once)
+    / its time; frac = achieved / measured peak.  A k-pass plan moves k x those bytes, so the per-pass view is kept beside it:
+    each pass's share of the step time (from per-pass CUDA events) and the same bytes over that time."""
+    ach = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    table, tname = traffic_table()
+    tr = table.get(wl) if isinstance(table, dict) else None
+    per_pass = None
+    if pass_ms_alone:
+        tot = sum(pass_ms_alone) or 1.0
+        per_pass = []
+        for j, x in enumerate(pass_ms_alone):
+            ms = ms_per_step * x / tot          # launch latency seen by events around a lone launch is overlapped in the timed region
+            a = alg_bytes / (ms * 1e-3) / 1e9
+            e = {"pass": j + 1, "ms": ms, "ms_timed_alone": x, "achieved": a, "frac": a / hbm_peak}
+            if isinstance(tr, dict) and isinstance(tr.get("per_pass"), list) and j < len(tr["per_pass"]):
+                e["traffic"] = tr["per_pass"][j]
+            per_pass.append(e)
+    total_traffic = None
+    if isinstance(tr, dict):
+        total_traffic = tr.get("total")
+    elif isinstance(tr, (int, float)):
+        total_traffic = tr
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+            "traffic": total_traffic, "traffic_source": (f"profiles/{tname}" if tname and tr is not None else None),
+            "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "units": units_note,
+            "per_pass": per_pass, "per_pass_frac": [e["frac"] for e in per_pass] if per_pass else None,
+            "passes": len(pass_ms_alone) if pass_ms_alone else None, "kernel": plan_desc,
+            "definition": "frac = algorithmic bytes of the whole transform (SURVEY.md 8d: 2 arrays x N x sizeof x (read + write)) / step time / measured "
+                          "copy peak; per_pass[j].frac = the same bytes / that pass's share of the step time (a k-pass plan is bounded by 1/k overall)"}
+
+
+class Ctx:
+    pass
+
+
+def setup(args):
     import torch
     import __graft_entry__ as ge
     with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
@@ -247,86 +296,216 @@ def run_ours(args):
     import phastft_b200 as pf
     from phastft_b200 import _lib
     from phastft_b200.sharding import max_over_ranks, shard_range
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
+    c = Ctx()
+    c.torch, c.pf, c.lib, c.shard_range = torch, pf, _lib, shard_range
+    c.world = int(os.environ.get("WORLD_SIZE", "1"))
+    c.rank = int(os.environ.get("RANK", "0"))
+    c.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if c.world != args.gpus and c.world > 1:
+        args.gpus = c.world
+    torch.cuda.set_device(c.local)
+    c.dev = torch.device("cuda", c.local)
+    c.dist = None
+    if c.world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        dist.init_process_group("nccl", rank=c.rank, world_size=c.world, device_id=c.dev)
+        c.dist = dist
 
     def barrier():
-        if dist is not None:
-            dist.barrier()
+        if c.dist is not None:
+            c.dist.barrier()
         torch.cuda.synchronize()
 
     def maxr(x):
-        return max_over_ranks(x, device=dev) if dist is not None else x
+        return max_over_ranks(x, device=c.dev) if c.dist is not None else x
+    c.barrier, c.maxr = barrier, maxr
+    c.hbm_peak, c.peak_src = peaks()
+    c.stream = torch.cuda.current_stream(c.dev)
+    c.cur_stream = lambda: C.c_void_p(torch.cuda.current_stream(c.dev).cuda_stream)   # inside a graph capture: the capture stream
+    c.gen = torch.Generator(device=c.dev)
+    c.gen.manual_seed(1234 + c.rank)
+    return c
 
-    hbm_peak, peak_src = peaks()
-    stream = torch.cuda.current_stream(dev)
 
-    def cur_stream():
-        # re-read every call: inside a CUDA-graph capture torch's current stream is the capture stream
-        return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+def timed(c, step, K, graph=None, group=1, graph_rem=None):
+    """EXACTLY K steps between barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    torch = c.torch
+    c.barrier()
+    launches0 = c.pf.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(c.stream)
+    if graph is not None:
+        for _ in range(K // group):
+            graph.replay()
+        if K % group:
+            if graph_rem is not None:
+                graph_rem.replay()
+            else:
+                for i in range(K % group):
+                    step(i)
+    else:
+        for i in range(K):
+            step(i)
+    ev1.record(c.stream)
+    torch.cuda.synchronize()
+    launched = c.pf.launch_count() - launches0
+    ms_total = c.maxr(ev0.elapsed_time(ev1))
+    c.barrier()
+    return ms_total / K, launched
+
+
+def per_pass_times(c, sfx, planner, get, batch, n, reps):
+    fprof = c.lib.fn("phastft_fft_dit_{s}_dev_profile", sfx)
+    pass_ms = (C.c_float * 3)()
+    npass = C.c_int(0)
+    acc = None
+    for i in range(reps):
+        a, b = get(i)
+        c.lib.check(fprof(planner._h, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), 1, batch, n, c.cur_stream(), pass_ms, C.byref(npass)))
+        cur = [pass_ms[j] for j in range(npass.value)]
+        acc = cur if acc is None else [x + y for x, y in zip(acc, cur)]
+    return [x / reps for x in acc]
+
+
+# ---- C4: 4096 x 2^16 f32, sharded over the ranks (strong scaling), the reference's caller loop examples/benchmark.rs:24-36 ----
+def measure_batch(c, K, W, with_e2e=True):
+    torch, pf, _lib = c.torch, c.pf, c.lib
+    n, total = 1 << 16, 4096
+    lo, hi = c.shard_range(total, c.rank, c.world)
+    nb = hi - lo
+    planner = pf.PlannerDit32(n, c.local)
+    if c.dist is not None:
+        planner.broadcast_tables(src=0)          # the one collective: every rank computes with rank 0's tables
+    planner.reserve(nb)
+    # the 4096 x 2^16 values come from ONE seeded stream, so shard contents do not depend on the number of ranks (SURVEY.md 8d)
+    g = torch.Generator(device=c.dev)
+    g.manual_seed(1234)
+    # (generating the whole 2 x 1 GiB batch on every rank and slicing keeps the contents rank-count independent)
+    full_re = torch.rand(total * n, dtype=torch.float32, device=c.dev, generator=g) * 2 - 1
+    full_im = torch.rand(total * n, dtype=torch.float32, device=c.dev, generator=g) * 2 - 1
+    re = full_re[lo * n:hi * n].clone(); im = full_im[lo * n:hi * n].clone()
+    f = _lib.fn("phastft_fft_dit_{s}_dev", "f32")
+
+    def step(i):
+        _lib.check(f(planner._h, C.c_void_p(re.data_ptr()), C.c_void_p(im.data_ptr()), 1, nb, n, c.cur_stream()))
+
+    # ---- shard parity: two transforms from each end of every rank's shard, recomputed on rank 0 from the seeded inputs with
+    # the same batched entry point (same kernels: a deterministic library must reproduce them bit for bit) ----
+    step(0)
+    torch.cuda.synchronize()
+    picks = sorted({0, 1, nb - 2, nb - 1} & set(range(nb)))
+    mine = torch.stack([torch.stack([re[k * n:(k + 1) * n], im[k * n:(k + 1) * n]]) for k in picks])       # [<=4, 2, n]
+    if c.dist is not None:
+        gathered = [torch.empty_like(mine) for _ in range(c.world)]
+        c.dist.all_gather(gathered, mine)
+    else:
+        gathered = [mine]
+    parity = None
+    if c.rank == 0:
+        idx = []
+        for r in range(c.world):
+            rlo, rhi = c.shard_range(total, r, c.world)
+            idx += [rlo + k for k in sorted({0, 1, rhi - rlo - 2, rhi - rlo - 1} & set(range(rhi - rlo)))]
+        slots = max(32, len(idx))                                      # >= 2^21 points: the call takes the batched kernels, like the shards
+        chk_re = torch.zeros(slots * n, dtype=torch.float32, device=c.dev); chk_im = torch.zeros_like(chk_re)
+        for j, k in enumerate(idx):
+            chk_re[j * n:(j + 1) * n] = full_re[k * n:(k + 1) * n]; chk_im[j * n:(j + 1) * n] = full_im[k * n:(k + 1) * n]
+        _lib.check(f(planner._h, C.c_void_p(chk_re.data_ptr()), C.c_void_p(chk_im.data_ptr()), 1, slots, n, c.cur_stream()))
+        torch.cuda.synchronize()
+        got = torch.cat([g_.to(c.dev) for g_ in gathered])               # [len(idx), 2, n]
+        ok = all(bool(torch.equal(chk_re[j * n:(j + 1) * n], got[j][0])) and bool(torch.equal(chk_im[j * n:(j + 1) * n], got[j][1])) for j in range(len(idx)))
+        parity = {"checked_transforms": len(idx), "bit_exact": ok,
+                  "what": "two transforms from each end of every rank's shard, gathered to rank 0 and recomputed there from the seeded inputs"}
+        del chk_re, chk_im
+    del full_re, full_im
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    ms_per_step, launched = timed(c, step, K)
+    value = total * n / (ms_per_step * 1e-3) / 1e9
+    alone = per_pass_times(c, "f32", planner, lambda b: (re, im), nb, n, 5)
+    alg = 2 * n * 4 * 2 * nb                   # this rank's shard; the fraction is per GPU (every rank streams its own HBM)
+    roof = roofline_block("batch_f32", alg, ms_per_step, alone, c.hbm_peak, c.peak_src, planner.describe(),
+                          f"per GPU: {nb} transforms x 16 N bytes")
+    out = {"metric": "Gpoint/s (complex), batch of 4096 x 2^16-point f32 forward FFTs sharded over the ranks", "value": value, "unit": "Gpoint/s",
+           "ms_per_step": ms_per_step, "steps": K, "warmup": W, "scaling": "strong", "transforms_per_rank": nb, "gpu_launches": int(launched),
+           "roofline": roof, "shard_parity": parity, "plan": planner.describe()}
+    if with_e2e:
+        h_re = torch.empty(nb * n, dtype=torch.float32).pin_memory(); h_im = torch.empty_like(h_re).pin_memory()
+        h_re.uniform_(-1, 1); h_im.uniform_(-1, 1)
+        a_re, a_im = h_re.numpy(), h_im.numpy()
+        fh = _lib.fn("phastft_fft_dit_{s}_batch_sharded_host", "f32")
+        arr = (C.c_void_p * 1)(planner._h)
+
+        def host_step():
+            _lib.check(fh(arr, 1, a_re.ctypes.data_as(C.c_void_p), a_im.ctypes.data_as(C.c_void_p), nb, n, 1))
+        host_step()
+        c.barrier()
+        ke = 3
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            host_step()
+        t_e = c.maxr(time.perf_counter() - t0)
+        c.barrier()
+        out["e2e"] = {"value": total * n / (t_e / ke) / 1e9, "unit": "Gpoint/s", "h2d_bytes_per_step": 2 * nb * n * 4, "d2h_bytes_per_step": 2 * nb * n * 4,
+                      "ms_per_step": t_e / ke * 1e3, "steps": ke,
+                      "api": "phastft_fft_dit_f32_batch_sharded_host (one call per step: the rank's whole shard, 3-slot H2D/FFT/D2H pipeline), pinned host memory"}
+    return out, planner
+
+
+def run_ours(args):
+    c = setup(args)
+    torch, pf, _lib = c.torch, c.pf, c.lib
+    world, rank, local, dev = c.world, c.rank, c.local, c.dev
     K, W = args.steps, max(args.warmup, 3)
     wl = args.workload
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1234 + rank)
+    sampler = ClockSampler(local)
+    sampler.start()
     extra = {}
+    roofline = e2e = None
+
+    if wl == "batch_f32":
+        out, planner = measure_batch(c, K, W, with_e2e=True)
+        clocks = sampler.stop()
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            _, _, cpu = cpu_reference_run(wl, steps=30, warmup=2, budget_s=25.0)
+        if rank == 0:
+            line = {"metric": f"Gpoint/s ({wl})", "value": out["value"], "unit": "Gpoint/s", "n_gpus": world, "steps": K, "warmup": W,
+                    "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                    "data": "synthetic", "config": workload_config(wl, world), "clocks": clocks, "e2e": out.get("e2e"),
+                    "gpu_launches": out["gpu_launches"], "roofline": out["roofline"], "shard_parity": out["shard_parity"], "cpu_baseline": cpu,
+                    "plan": out["plan"]}
+            print(json.dumps(line), flush=True)
+        if c.dist is not None:
+            c.dist.destroy_process_group()
+        return 0
 
     if wl in ("c2c_f64_2p20", "c2c_f64_2p26"):
         n = 1 << (20 if wl == "c2c_f64_2p20" else 26)
         planner = pf.PlannerDit64(n, local)
-        if dist is not None:
+        if c.dist is not None:
             planner.broadcast_tables(src=0)          # the one collective of the whole job
         nbuf = 16 if n == (1 << 20) else 2
-        nbuf = max(nbuf, -(-(K + W) // 90)) if n == (1 << 20) else nbuf
-        bufs_re = [(torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1) for _ in range(nbuf)]
-        bufs_im = [(torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1) for _ in range(nbuf)]
-        keep = [(b.clone(), c.clone()) for b, c in zip(bufs_re[:2], bufs_im[:2])] if n == (1 << 20) else None
+        bufs_re = [(torch.rand(n, dtype=torch.float64, device=dev, generator=c.gen) * 2 - 1) for _ in range(nbuf)]
+        bufs_im = [(torch.rand(n, dtype=torch.float64, device=dev, generator=c.gen) * 2 - 1) for _ in range(nbuf)]
         f = _lib.fn("phastft_fft_dit_{s}_dev", "f64")
 
         def step(i):
             b = i % nbuf
-            _lib.check(f(planner._h, C.c_void_p(bufs_re[b].data_ptr()), C.c_void_p(bufs_im[b].data_ptr()), 1, 1, n, cur_stream()))
+            _lib.check(f(planner._h, C.c_void_p(bufs_re[b].data_ptr()), C.c_void_p(bufs_im[b].data_ptr()), 1, 1, n, c.cur_stream()))
 
         def reset():
             for b in range(nbuf):
-                bufs_re[b].uniform_(-1, 1, generator=gen); bufs_im[b].uniform_(-1, 1, generator=gen)
+                bufs_re[b].uniform_(-1, 1, generator=c.gen); bufs_im[b].uniform_(-1, 1, generator=c.gen)
         points_per_step = n
-        alg_bytes_per_pass = 2 * n * 8 * 2            # each planar array read once + written once
+        alg_bytes = 2 * n * 8 * 2                     # each planar array read once + written once (SURVEY.md 8d)
         dtype = "f64"
-        prof = ("f64", planner, lambda b: (bufs_re[b % nbuf], bufs_im[b % nbuf]), 1, n)
-    elif wl == "batch_f32":
-        n, total = 1 << 16, 4096
-        lo, hi = shard_range(total, rank, world)
-        nb = hi - lo
-        planner = pf.PlannerDit32(n, local)
-        if dist is not None:
-            planner.broadcast_tables(src=0)
-        re = torch.rand(nb * n, dtype=torch.float32, device=dev, generator=gen) * 2 - 1
-        im = torch.rand(nb * n, dtype=torch.float32, device=dev, generator=gen) * 2 - 1
-        f = _lib.fn("phastft_fft_dit_{s}_dev", "f32")
-
-        def step(i):
-            _lib.check(f(planner._h, C.c_void_p(re.data_ptr()), C.c_void_p(im.data_ptr()), 1, nb, n, cur_stream()))
-
-        def reset():
-            re.uniform_(-1, 1, generator=gen); im.uniform_(-1, 1, generator=gen)
-        points_per_step = nb * n
-        dtype = "f32"
-        prof = ("f32", planner, lambda b: (re, im), nb, n)
-        alg_bytes_per_pass = None
+        units_note = "one transform: 32 N bytes"
     elif wl == "r2c_f64_2p24":
         n = 1 << 24
         planner = pf.PlannerR2c64(n, local)
-        x = torch.rand(n, dtype=torch.float64, device=dev, generator=gen) * 2 - 1
+        x = torch.rand(n, dtype=torch.float64, device=dev, generator=c.gen) * 2 - 1
         y = torch.empty_like(x)
         sre = torch.empty(n // 2 + 1, dtype=torch.float64, device=dev); sim = torch.empty_like(sre)
         scr_re = torch.empty(n // 2, dtype=torch.float64, device=dev); scr_im = torch.empty_like(scr_re)
@@ -338,27 +517,31 @@ def run_ours(args):
         def reset():
             pass
         points_per_step = n
+        # r2c reads 8 N and writes 2 x 8 (N/2 + 1); c2r the reverse
+        alg_bytes = 2 * (8 * n + 16 * (n // 2 + 1))
         dtype = "f64"
-        prof = None
-        alg_bytes_per_pass = None
+        units_note = "one r2c + one c2r of 2^24 reals: 2 x (8 N + 16 (N/2 + 1)) bytes"
     else:
         raise SystemExit(f"unknown workload {wl}")
 
     # ---- warm-up, then EXACTLY K timed steps between barrier+synchronize -------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
     for i in range(W):
         step(i)
     torch.cuda.synchronize()
-    # The 2^20 step is ~10 us of GPU work issued by one C-ABI call (2 kernel launches): capture the
-    # rotation over the NBUF signals into a CUDA graph so the host launch path cannot be the bottleneck.
-    graph, group = None, 1
+    # The 2^20 step is ~19 us of GPU work issued by one C-ABI call (2 kernel launches): capture the rotation over the NBUF
+    # signals into a CUDA graph (and the K mod NBUF leftover steps into a second one) so the host launch path is never the bottleneck.
+    graph, group, graph_rem = None, 1, None
     if wl == "c2c_f64_2p20" and not args.no_graph:
         group = nbuf
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             for i in range(group):
                 step(i)
+        if K % group:
+            graph_rem = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_rem):
+                for i in range(K % group):
+                    step(i)
         torch.cuda.synchronize()
     # extra untimed load (~0.3 s) so the clocks are at their loaded level when timing starts
     t_pre = time.perf_counter()
@@ -369,115 +552,42 @@ def run_ours(args):
             step(0)
         torch.cuda.synchronize()
     reset()
-    barrier()
-    launches0 = pf.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
+    ms_per_step, launches = timed(c, step, K, graph, group, graph_rem)
     if graph is not None:
-        for _ in range(K // group):
-            graph.replay()
-        for i in range(K % group):
-            step(i)
-    else:
-        for i in range(K):
-            step(i)
-    ev1.record(stream)
-    torch.cuda.synchronize()
-    launches = pf.launch_count() - launches0
-    if graph is not None:
-        launches += (K // group) * group * planner_passes(planner)   # graph replays launch kernels without entering the library
-    ms_total = maxr(ev0.elapsed_time(ev1))
-    barrier()
-    ms_per_step = ms_total / K
-    value = world * points_per_step / (ms_per_step * 1e-3) / 1e9 if wl != "batch_f32" else 4096 * (1 << 16) / (ms_per_step * 1e-3) / 1e9
+        launches += K * planner_passes(planner)          # graph replays launch kernels without entering the library
+    value = world * points_per_step / (ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel: per-pass CUDA-event times, live, on the launching stream ----
-    roofline = None
-    if prof is not None:
-        sfx, pl_, get, batch_, n_ = prof
-        fprof = _lib.fn("phastft_fft_dit_{s}_dev_profile", sfx)
-        pass_ms = (C.c_float * 3)()
-        npass = C.c_int(0)
-        acc = None
-        reps = 40 if wl != "c2c_f64_2p26" else 10
+    # ---- roofline: whole-transform fraction from the timed region; per-pass split from CUDA events, live, on the launching stream ----
+    alone = None
+    if wl != "r2c_f64_2p24":
         reset()
-        # extra load so the clocks sampler sees a loaded GPU for >= ~1 s in total
-        for i in range(reps):
-            a, b = get(i)
-            _lib.check(fprof(pl_._h, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), 1, batch_, n_, cur_stream(), pass_ms, C.byref(npass)))
-            cur = [pass_ms[j] for j in range(npass.value)]
-            acc = cur if acc is None else [x + y for x, y in zip(acc, cur)]
-        avg_alone = [x / reps for x in acc]
-        # Per-launch duration over the TIMED REGION: the step time apportioned by each pass's share of the
-        # per-pass CUDA-event times (events around a lone launch also see its launch latency, which the
-        # back-to-back launches of the timed region overlap).
-        tot_alone = sum(avg_alone) or 1.0
-        avg = [ms_per_step * x / tot_alone for x in avg_alone]
-        dom = max(range(len(avg)), key=lambda j: avg[j])
-        esz = 8 if sfx == "f64" else 4
-        # algorithmic bytes of ONE launch: it reads each planar array of its chunk once and writes it once
-        chunk = batch_
-        if batch_ > 1:
-            chunk = max(1, min(batch_, (4 << 30) // (n_ * 2 * esz)))
-        bytes_launch = 2 * n_ * esz * 2 * chunk
-        ach = bytes_launch / (avg[dom] * 1e-3) / 1e9
-        traffic = None
-        tfile = ROOT / "profiles" / "traffic.json"
-        if tfile.exists():
-            try:
-                traffic = json.loads(tfile.read_text()).get(wl)
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": traffic, "peak_source": peak_src, "kernel": f"pass {dom + 1}/{len(avg)} of {pl_.describe()}",
-                    "algorithmic_bytes_per_launch": bytes_launch, "pass_ms": avg, "pass_ms_timed_alone": avg_alone,
-                    "note": "achieved = algorithmic bytes of the dominant pass / its duration in the timed region (step time x the pass's share of the per-pass CUDA-event times); "
-                            "a k-pass plan moves k x the compulsory 32N bytes, so the whole-transform fraction is value-based: "
-                            f"{(world and 1) * 2 * n_ * esz * 2 * (batch_ if batch_ > 1 else 1) / (ms_per_step * 1e-3) / 1e9 / hbm_peak:.3f}"}
-    clocks = sampler.stop()
+        alone = per_pass_times(c, "f64", planner, lambda b: (bufs_re[b % nbuf], bufs_im[b % nbuf]), 1, n, 40 if wl == "c2c_f64_2p20" else 10)
+    roofline = roofline_block(wl, alg_bytes, ms_per_step, alone, c.hbm_peak, c.peak_src,
+                              planner.describe() if hasattr(planner, "describe") else "r2c: half-length c2c passes + untangle; c2r: preprocess + passes", units_note)
 
     # ---- e2e: the reference-facing host-slice call, pinned host buffers, H2D + D2H inside the timed region ----
-    e2e = None
-    if wl in ("c2c_f64_2p20", "c2c_f64_2p26", "batch_f32"):
-        if wl == "batch_f32":
-            lo, hi = shard_range(4096, rank, world)
-            nb = hi - lo
-            h_re = torch.empty(nb * n, dtype=torch.float32).pin_memory(); h_im = torch.empty_like(h_re).pin_memory()
-            h_re.uniform_(-1, 1); h_im.uniform_(-1, 1)
-            a_re, a_im = h_re.numpy(), h_im.numpy()
-            fh = _lib.fn("phastft_fft_dit_{s}_batch_sharded_host", "f32")
-            arr = (C.c_void_p * 1)(planner._h)
+    if wl in ("c2c_f64_2p20", "c2c_f64_2p26"):
+        h_re = torch.empty(n, dtype=torch.float64).pin_memory(); h_im = torch.empty_like(h_re).pin_memory()
+        h_re.uniform_(-1, 1); h_im.uniform_(-1, 1)
+        a_re, a_im = h_re.numpy(), h_im.numpy()
+        pristine = (a_re.copy(), a_im.copy())
 
-            def host_step():
-                _lib.check(fh(arr, 1, a_re.ctypes.data_as(C.c_void_p), a_im.ctypes.data_as(C.c_void_p), nb, n, 1))
-            bytes_one_way = 2 * nb * n * 4
-            e_points = 4096 * n
-        else:
-            h_re = torch.empty(n, dtype=torch.float64).pin_memory(); h_im = torch.empty_like(h_re).pin_memory()
-            h_re.uniform_(-1, 1); h_im.uniform_(-1, 1)
-            a_re, a_im = h_re.numpy(), h_im.numpy()
-            pristine = (a_re.copy(), a_im.copy())
-
-            def host_step():
-                pf.fft_64_dit_with_planner(a_re, a_im, pf.Direction.Forward, planner)
-            bytes_one_way = 2 * n * 8
-            e_points = world * n
+        def host_step():
+            pf.fft_64_dit_with_planner(a_re, a_im, pf.Direction.Forward, planner)
+        bytes_one_way = 2 * n * 8
         ke = max(5, min(K, 30))
         for _ in range(3):
             host_step()
-        if wl != "batch_f32":
-            a_re[:] = pristine[0]; a_im[:] = pristine[1]
-        barrier()
+        a_re[:] = pristine[0]; a_im[:] = pristine[1]
+        c.barrier()
         t0 = time.perf_counter()
         for _ in range(ke):
             host_step()                      # synchronous: returns after the D2H copy has landed
-        t_e = maxr(time.perf_counter() - t0)
-        barrier()
-        e2e = {"value": e_points / (t_e / ke) / 1e9, "unit": "Gpoint/s", "h2d_bytes_per_step": bytes_one_way,
+        t_e = c.maxr(time.perf_counter() - t0)
+        c.barrier()
+        e2e = {"value": world * n / (t_e / ke) / 1e9, "unit": "Gpoint/s", "h2d_bytes_per_step": bytes_one_way,
                "d2h_bytes_per_step": bytes_one_way, "ms_per_step": t_e / ke * 1e3, "steps": ke,
-               "api": ("phastft_fft_dit_f32_batch_sharded_host (one call per step: the whole shard, 3-slot H2D/FFT/D2H pipeline), pinned host memory"
-                       if wl == "batch_f32" else
-                       "phastft_fft_dit_f64_host (= fft_64_dit_with_planner on host slices; one synchronous call per step), pinned host memory")}
+               "api": "phastft_fft_dit_f64_host (= fft_64_dit_with_planner on host slices; one synchronous call per step), pinned host memory"}
         if wl == "c2c_f64_2p20":
             # the same job -- a stream of independent 2^20 transforms in host memory -- handed to the library as ONE
             # batched call, so H2D of signal j+1, the FFT of j and D2H of j-1 overlap (both PCIe directions busy)
@@ -492,15 +602,24 @@ def run_ours(args):
                 _lib.check(fhb(arr1, 1, b_re.ctypes.data_as(C.c_void_p), b_im.ctypes.data_as(C.c_void_p), nsig, n, 1))
             stream_step()
             s_re.uniform_(-1, 1); s_im.uniform_(-1, 1)
-            barrier()
+            c.barrier()
             t0 = time.perf_counter()
             for _ in range(3):
                 stream_step()
-            t_s = maxr(time.perf_counter() - t0)
-            barrier()
+            t_s = c.maxr(time.perf_counter() - t0)
+            c.barrier()
             e2e["pipelined"] = {"value": world * 3 * nsig * n / t_s / 1e9, "unit": "Gpoint/s", "transforms_per_call": nsig,
                                 "ms_per_transform": t_s / (3 * nsig) * 1e3,
                                 "api": "phastft_fft_dit_f64_batch_sharded_host: 32 host-resident 2^20 signals per call, 3-slot H2D/FFT/D2H pipeline"}
+            del s_re, s_im
+
+    # ---- the batched configuration of the north star beside the headline: 4096 x 2^16 f32 sharded over the N ranks ----
+    batched = None
+    if wl == "c2c_f64_2p20" and not args.no_batched:
+        del bufs_re, bufs_im
+        torch.cuda.empty_cache()
+        batched, _ = measure_batch(c, 20, 3, with_e2e=True)
+    clocks = sampler.stop()
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ------------------------------------
     cpu = None
@@ -511,13 +630,14 @@ def run_ours(args):
         line = {
             "metric": METRIC if wl == "c2c_f64_2p20" else f"Gpoint/s ({wl})", "value": value, "unit": "Gpoint/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong" if wl == "batch_f32" else "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": workload_config(wl, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu, "plan": planner.describe() if hasattr(planner, "describe") else None,
+            "batched": batched,
         }
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if c.dist is not None:
+        c.dist.destroy_process_group()
     return 0
 
 
@@ -530,6 +650,7 @@ def main():
     ap.add_argument("--workload", default="c2c_f64_2p20", choices=["c2c_f64_2p20", "c2c_f64_2p26", "batch_f32", "r2c_f64_2p24"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every step through the C ABI instead of replaying a captured CUDA graph")
+    ap.add_argument("--no-batched", action="store_true", help="skip the 4096 x 2^16 f32 sharded measurement that the default workload adds as `batched`")
     args = ap.parse_args()
     # defaults sized so the timed region lasts ~0.2-0.5 s (clock sampling needs that) and a run takes < 2 min
     dflt = {"c2c_f64_2p20": (20000, 200), "c2c_f64_2p26": (100, 5), "batch_f32": (100, 5), "r2c_f64_2p24": (200, 10)}[args.workload]

@@ -32,6 +32,21 @@ int main() {
     fft_64_dit(re, im, Direction::Forward);
     for (double v : re) fails += std::fabs(v - 1.0) > 1e-12;
     fails += !panics_with([] { std::vector<double> a(16), b(8); PlannerDit64 p(16); fft_64_dit_with_planner(a, b, Direction::Forward, p); }, "reals.len() == imags.len()");
+    {   // additive surface: describe / reserve / batch == loop over transforms (bit-exact below the batched-kernel threshold)
+        const std::size_t n = 256, batch = 5, stride = n + 8;
+        PlannerDit32 p(n);
+        fails += p.num_points() != n || p.describe().find("n=2^8") == std::string::npos;
+        p.reserve(batch);
+        std::vector<float> bre(batch * stride), bim(batch * stride);
+        for (std::size_t i = 0; i < bre.size(); ++i) { bre[i] = std::sin(0.37f * i); bim[i] = std::cos(0.11f * i); }
+        std::vector<float> lre = bre, lim = bim;
+        fft_32_dit_batch(bre, bim, Direction::Forward, p, batch, stride);
+        for (std::size_t b = 0; b < batch; ++b) {
+            std::vector<float> a(lre.begin() + b * stride, lre.begin() + b * stride + n), c(lim.begin() + b * stride, lim.begin() + b * stride + n);
+            fft_32_dit_with_planner(a, c, Direction::Forward, p);
+            for (std::size_t i = 0; i < n; ++i) fails += a[i] != bre[b * stride + i] || c[i] != bim[b * stride + i];
+        }
+    }
     std::printf("gpu checks: %d failures\n", fails);
     return fails;
 }

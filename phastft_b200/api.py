@@ -205,6 +205,40 @@ class PlannerR2c32(_PlannerR2c):
     _sfx, _dtype = "f32", np.float32
 
 
+# The convenience functions plan per call like the reference (lib.rs:180-183); building a plan and allocating its workspace
+# per call costs far more than the transform, and destroying a plan while its kernels are still queued relies on cudaFree's
+# implicit synchronisation -- so the most recent one-shot planner per (class, size, device) is kept, like the C library
+# does for host slices (phastft_*_oneshot).
+_ONESHOT_PLANNERS: dict = {}
+
+
+def _oneshot_planner(cls, n: int, device: int):
+    key = (cls.__name__, device)
+    hit = _ONESHOT_PLANNERS.get(key)
+    if hit is not None and hit[0] == n:
+        return hit[1]
+    planner = cls(n, device)           # raises the reference's panic for an invalid size before anything is cached
+    if hit is not None and _is_torch_available():
+        import torch
+        torch.cuda.synchronize(device)     # the replaced planner may still have work queued
+    _ONESHOT_PLANNERS[key] = (n, planner)
+    return planner
+
+
+def _is_torch_available() -> bool:
+    try:
+        import torch  # noqa: F401
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def oneshot_cache_clear() -> None:
+    """Drop the planners kept for the convenience functions (here and inside the C library)."""
+    _ONESHOT_PLANNERS.clear()
+    _lib.lib.phastft_oneshot_cache_clear()
+
+
 # ----------------------------------------------------------------------------------------------
 # c2c
 # ----------------------------------------------------------------------------------------------
@@ -240,7 +274,7 @@ def _fft_dit(sfx, dtype, planner_cls, reals, imags, direction, device=0):
         pi, ni = _np_ptr(imags, dtype, True)
         check(fn("phastft_fft_dit_{s}_oneshot", sfx)(pr, nr, pi, ni, int(direction), int(device)))
         return
-    planner = planner_cls(reals.numel(), reals.device.index or 0)
+    planner = _oneshot_planner(planner_cls, reals.numel(), reals.device.index or 0)
     _fft_dit_with_planner(sfx, dtype, reals, imags, direction, planner)
 
 
@@ -348,7 +382,7 @@ def fft_64_interleaved_with_planner(signal, direction, planner: PlannerDit64):
 
 def fft_64_interleaved(signal, direction, device: int = 0):
     n = signal.numel() if _is_torch(signal) else signal.size
-    _interleaved("f64", np.float64, np.complex128, signal, direction, PlannerDit64(n, device))
+    _interleaved("f64", np.float64, np.complex128, signal, direction, _oneshot_planner(PlannerDit64, n, device))
 
 
 def fft_32_interleaved_with_planner_and_opts(signal, direction, planner: PlannerDit32, opts: Options | None = None):
@@ -361,7 +395,7 @@ def fft_32_interleaved_with_planner(signal, direction, planner: PlannerDit32):
 
 def fft_32_interleaved(signal, direction, device: int = 0):
     n = signal.numel() if _is_torch(signal) else signal.size
-    _interleaved("f32", np.float32, np.complex64, signal, direction, PlannerDit32(n, device))
+    _interleaved("f32", np.float32, np.complex64, signal, direction, _oneshot_planner(PlannerDit32, n, device))
 
 
 # ----------------------------------------------------------------------------------------------
@@ -436,7 +470,7 @@ def r2c_fft_f64(input_re, output_re, output_im, device: int = 0) -> None:
         pi, ni = _np_ptr(output_im, np.float64, True)
         check(fn("phastft_r2c_{s}_oneshot", "f64")(px, nx, pr, nr, pi, ni, int(device)))
         return
-    _r2c_with_planner("f64", np.float64, input_re, output_re, output_im, PlannerR2c64(_len(input_re), _dev_of(input_re, device)))
+    _r2c_with_planner("f64", np.float64, input_re, output_re, output_im, _oneshot_planner(PlannerR2c64, _len(input_re), _dev_of(input_re, device)))
 
 
 def r2c_fft_f64_with_planner(input_re, output_re, output_im, planner: PlannerR2c64) -> None:
@@ -452,7 +486,7 @@ def c2r_fft_f64(input_re, input_im, output, device: int = 0) -> None:
         po, no = _np_ptr(output, np.float64, True)
         check(fn("phastft_c2r_{s}_oneshot", "f64")(pr, nr, pi, ni, po, no, int(device)))
         return
-    _c2r_with_planner("f64", np.float64, input_re, input_im, output, PlannerR2c64(_len(output), _dev_of(output, device)))
+    _c2r_with_planner("f64", np.float64, input_re, input_im, output, _oneshot_planner(PlannerR2c64, _len(output), _dev_of(output, device)))
 
 
 def c2r_fft_f64_with_planner(input_re, input_im, output, planner: PlannerR2c64) -> None:
@@ -473,7 +507,7 @@ def r2c_fft_f32(input_re, output_re, output_im, device: int = 0) -> None:
         pi, ni = _np_ptr(output_im, np.float32, True)
         check(fn("phastft_r2c_{s}_oneshot", "f32")(px, nx, pr, nr, pi, ni, int(device)))
         return
-    _r2c_with_planner("f32", np.float32, input_re, output_re, output_im, PlannerR2c32(_len(input_re), _dev_of(input_re, device)))
+    _r2c_with_planner("f32", np.float32, input_re, output_re, output_im, _oneshot_planner(PlannerR2c32, _len(input_re), _dev_of(input_re, device)))
 
 
 def r2c_fft_f32_with_planner(input_re, output_re, output_im, planner: PlannerR2c32) -> None:
@@ -489,7 +523,7 @@ def c2r_fft_f32(input_re, input_im, output, device: int = 0) -> None:
         po, no = _np_ptr(output, np.float32, True)
         check(fn("phastft_c2r_{s}_oneshot", "f32")(pr, nr, pi, ni, po, no, int(device)))
         return
-    _c2r_with_planner("f32", np.float32, input_re, input_im, output, PlannerR2c32(_len(output), _dev_of(output, device)))
+    _c2r_with_planner("f32", np.float32, input_re, input_im, output, _oneshot_planner(PlannerR2c32, _len(output), _dev_of(output, device)))
 
 
 def c2r_fft_f32_with_planner(input_re, input_im, output, planner: PlannerR2c32) -> None:

@@ -23,6 +23,7 @@
 //              digit-reversing transpose, written as C-element contiguous runs.
 //   KIND_ROW   whole transform in one CTA (N <= 4096 f64 / 8192 f32): rows contiguous in and out.
 #pragma once
+#include <cuda.h>
 #include <type_traits>
 
 #include "fft_device.cuh"
@@ -60,6 +61,12 @@ struct PassParams {
     // cluster exchange (XCH = 1 producer only): the consuming pass's tile is [CB rows][P2 points]
     int xch_log2P2;                // log2 of the consumer's row length (= its R)
     int xch_log2CB;                // log2 of the consumer's rows per CTA (= its C)
+    // ring of workspace slots (fft_pipe2_kernel): transform b's intermediate lives in slot b % ring (ring a power of two; 0 = none)
+    int out_ring;                  // KIND_COL: applied to the batch index of the OUTPUT address
+    int in_ring;                   // KIND_TRANS: applied to the batch index of the INPUT address
+    // TMA tile input (MODE_TMA_IN only): one tensor map per planar array, dims {B columns, R rows, batch}
+    alignas(64) CUtensorMap tmap_re;
+    alignas(64) CUtensorMap tmap_im;
 };
 
 // Shared-memory tile addressing (units: complex elements).
@@ -116,18 +123,54 @@ __device__ __forceinline__ void st_cluster(unsigned addr, const float2& v) {
     asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
 
-// XCH (cluster exchange role of this pass inside fft_cluster2_kernel, see there):
+// TMA / mbarrier helpers (sm_90+; SASS: UTMALDG for the tensor copy, UBLKCP for the 1-D bulk copy, SYNCS for the mbarrier)
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+// 3-D tensor tile (box fixed in the map) global -> shared, completion counted on `mbar`
+__device__ __forceinline__ void tma_load_3d(unsigned smem_dst, const CUtensorMap* map, int x, int y, int z, unsigned mbar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
+}
+// contiguous bytes global -> shared (16-byte aligned, size a multiple of 16)
+__device__ __forceinline__ void bulk_load_1d(unsigned smem_dst, const void* gsrc, unsigned bytes, unsigned mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_dst), "l"(gsrc), "r"(bytes), "r"(mbar) : "memory");
+}
+
+// XCH (how this pass gets its input tile / where its last stage puts its results):
 //   0  plain pass: global memory in, global memory out
 //   1  producer (KIND_COL): the LAST stage does not store to global memory; every thread keeps its results in
 //      registers across a cluster barrier and then scatters them into the shared-memory tiles of the CTAs that own
 //      the rows in the next pass, in the layout [row c'][t] that pass's global loads would have read
 //   2  consumer (KIND_TRANS): stage 1 reads that tile instead of global memory (all threads first, then a
 //      __syncthreads, then the tile is overwritten in the pass's own layout)
+//   3  TMA tile input (KIND_COL, first pass, planar input): one thread issues cp.async.bulk.tensor copies of the tile's
+//      R x C boxes of the re and im arrays straight into the tile's shared memory (no per-thread address generation, no
+//      LSU sector waste on the 32-byte runs of a 4-column f64 tile -- which is what lets a 1024-row tile be 64 KB and three
+//      CTAs share an SM); the threads wait on the mbarrier, read their stage-1 inputs out of the landing zone, and go on as usual
+//   4  bulk tile input (KIND_TRANS, interleaved intermediates): the tile's C rows are contiguous in the workspace -- C
+//      cp.async.bulk copies land them as [c][t], then as mode 2
+enum { MODE_PLAIN = 0, MODE_XCH_PRODUCE = 1, MODE_XCH_CONSUME = 2, MODE_TMA_IN = 3, MODE_BULK_IN = 4 };
 template <typename T, class RL, int C, int NT, int KIND, int XCH = 0, int VARIANT = 0>
 struct PassKernel {
     static constexpr int S = RL::S;
     static constexpr int R = RL::R();
     static constexpr int LOG2R = ilog2_c(R);
+    static constexpr int TILE_C = C;               // tile width (columns for COL, rows for TRANS / ROW)
     static constexpr int R1 = RL::rad(0);          // first-stage radix
     static constexpr int M = R / R1;               // stage-1 tasks per column
     static constexpr int LOG2C = ilog2_c(C);
@@ -135,10 +178,15 @@ struct PassKernel {
     // shared memory: tile (only if S >= 2) + Um[M] + G[C][R1]
     static constexpr int TILE_ELEMS = (S >= 2) ? R * C : 0;
     static constexpr int G_ELEMS = (KIND == KIND_TRANS) ? C * R1 : R1;
-    static constexpr size_t SMEM_BYTES = sizeof(cx<T>) * (size_t)(TILE_ELEMS + M + G_ELEMS);
+    static constexpr bool ASYNC_IN = (XCH == MODE_TMA_IN || XCH == MODE_BULK_IN);
+    static constexpr size_t TABLE_END = sizeof(cx<T>) * (size_t)(TILE_ELEMS + M + G_ELEMS);
+    static constexpr size_t MBAR_OFF = (TABLE_END + 15) & ~size_t(15);
+    static constexpr size_t SMEM_BYTES = ASYNC_IN ? MBAR_OFF + 16 : TABLE_END;
     static_assert(XCH == 0 || S >= 2, "an exchanging pass needs a shared-memory tile");
     static_assert(XCH != 1 || KIND == KIND_COL, "the producer of a cluster exchange is a COL pass");
     static_assert(XCH != 2 || KIND == KIND_TRANS, "the consumer of a cluster exchange is a TRANS pass");
+    static_assert(XCH != MODE_TMA_IN || (KIND == KIND_COL && C * sizeof(T) >= 16), "TMA tile input: COL pass, rows of >= 16 bytes");
+    static_assert(XCH != MODE_BULK_IN || KIND == KIND_TRANS, "bulk tile input: TRANS pass");
 
     // ---- global element access -------------------------------------------------------------
     static __device__ __forceinline__ void gload(const PassParams<T>& p, long long idx, T& re, T& im) {
@@ -310,7 +358,7 @@ struct PassKernel {
     // Threads with threadIdx.x >= NT (a fused launch whose other pass needs more threads) take part in
     // the barriers only: their task index starts beyond every task count.
     static __device__ __forceinline__ void body(const PassParams<T>& p, unsigned tile_index) {
-        extern __shared__ __align__(16) unsigned char smem_raw[];
+        extern __shared__ __align__(128) unsigned char smem_raw[];
         cx<T>* tile = reinterpret_cast<cx<T>*>(smem_raw);
         cx<T>* s_um = tile + TILE_ELEMS;   // [M]       per-CTA  W_L^(kp*B*m')
         cx<T>* s_g = s_um + M;             // [C][R1] or [R1]     W_L^(kp(c)*M*B*i)
@@ -319,9 +367,11 @@ struct PassKernel {
         // Programmatic dependent launch (sm_90+): this grid may have been scheduled while the previous
         // pass is still draining; wait for its memory to be visible before touching global data, and
         // let the next pass's CTAs be scheduled as soon as every CTA of this grid is resident.
+        // With an asynchronous tile input only the thread that issues the copies waits: the others build the
+        // twiddle tables meanwhile and meet the data at the mbarrier (every later access depends on that data).
         if (p.pdl) {
-            asm volatile("griddepcontrol.wait;" ::: "memory");
             asm volatile("griddepcontrol.launch_dependents;");
+            if constexpr (!ASYNC_IN) asm volatile("griddepcontrol.wait;" ::: "memory");
         }
         long long in_base, out_base, out_kstride;
         long long in_rstride;          // element stride of the tile row index r (COL) / 1 (ROW, TRANS)
@@ -340,7 +390,7 @@ struct PassKernel {
             const int batch = rest >> p.log2A;
             const long long off = ((long long)a << (LOG2R + p.log2B)) + ((long long)bt << LOG2C);
             in_base = (long long)batch * p.in_bstride + off;
-            out_base = (long long)batch * p.out_bstride + off;
+            out_base = (long long)(p.out_ring ? (batch & (p.out_ring - 1)) : batch) * p.out_bstride + off;
             in_rstride = 1LL << p.log2B;
             in_cstride = 1;
             out_kstride = in_rstride;
@@ -356,7 +406,7 @@ struct PassKernel {
             const int rest = tmp & ((1 << log2restn) - 1);
             const int batch = tmp >> log2restn;
             const int k0 = kt << LOG2C;
-            in_base = (long long)batch * p.in_bstride + ((((long long)k0 << log2restn) + rest) << LOG2R);
+            in_base = (long long)(p.in_ring ? (batch & (p.in_ring - 1)) : batch) * p.in_bstride + ((((long long)k0 << log2restn) + rest) << LOG2R);
             in_rstride = 1;
             in_cstride = 1LL << (log2restn + LOG2R);
             // out[(k0 + c) + R1*rest + A*kr]
@@ -375,18 +425,48 @@ struct PassKernel {
             out_kstride = 1;
         }
 
+        // ---- asynchronous tile input: thread 0 puts the whole tile in flight --------------------------------------
+        [[maybe_unused]] const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem_raw + MBAR_OFF);
+        if constexpr (ASYNC_IN) {
+            if (tid == 0) {
+                mbar_init(mbar, 1);
+                if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+                mbar_expect_tx(mbar, (unsigned)(TILE_ELEMS * sizeof(cx<T>)));
+                const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
+                if constexpr (XCH == MODE_TMA_IN) {
+                    // landing zone: re plane [R][C] then im plane [R][C]; boxes of at most 256 rows
+                    constexpr int BOX_ROWS = R < 256 ? R : 256;
+                    const int blkq = (int)(tile_index + (unsigned)p.blk_offset);
+                    const int col0 = (blkq & ((1 << (p.log2B - LOG2C)) - 1)) << LOG2C;
+                    const int bz = blkq >> (p.log2B - LOG2C);          // first pass: log2A == 0, the rest is the batch index
+#pragma unroll
+                    for (int r0 = 0; r0 < R; r0 += BOX_ROWS) {
+                        tma_load_3d(tile_s + (unsigned)(r0 * C * sizeof(T)), &p.tmap_re, col0, r0, bz, mbar);
+                        tma_load_3d(tile_s + (unsigned)((R + r0) * C * sizeof(T)), &p.tmap_im, col0, r0, bz, mbar);
+                    }
+                } else {
+                    const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in_re) + in_base;
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        bulk_load_1d(tile_s + (unsigned)(c * R * sizeof(cx<T>)), src + (long long)c * in_cstride, (unsigned)(R * sizeof(cx<T>)), mbar);
+                }
+            }
+        }
+
         // ---- PRELOAD: when every thread owns exactly one stage-1 task, issue its global loads NOW so
         // they are in flight while the twiddle tables below are built (their two-level lookups are two
         // dependent L2 round trips that would otherwise sit in front of the first data load).
         constexpr bool PRELOAD = (M * C <= NT);
-        static_assert(XCH != 2 || PRELOAD, "the consumer's stage 1 must be a single trip (every thread holds its task's inputs across the barrier)");
+        static_assert((XCH != 2 && !ASYNC_IN) || PRELOAD, "a pass that reads its input out of its own tile must do stage 1 in a single trip (every thread holds its task's inputs across the barrier)");
         T pre_r[PRELOAD ? R1 : 1], pre_i[PRELOAD ? R1 : 1];
         if constexpr (PRELOAD) {
             const int t = tid;
             if (t < M * C) {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
-                if constexpr (XCH == 2) {
+                if constexpr (ASYNC_IN) {
+                    // filled in below, once the tile has landed
+                } else if constexpr (XCH == 2) {
                     // the previous pass's CTAs left this tile as [c][t], t = mp + i*M (what the global loads would have read)
                     const cx<T>* src = tile + c * R + mp;
 #pragma unroll
@@ -426,8 +506,27 @@ struct PassKernel {
                 vreg = to_cx<T>(p.tw2.get(e << p.tw_shift));
             }
             __syncthreads();
-        } else if constexpr (XCH == 2) {
+        } else if constexpr (XCH == 2 || ASYNC_IN) {
             __syncthreads();     // every thread has read its inputs out of the exchanged tile before stage 1 overwrites it
+        }                        // (asynchronous input: thread 0's mbarrier init is visible to all)
+        if constexpr (ASYNC_IN) {
+            mbar_wait(mbar, 0);
+            const int t = tid;
+            if (t < M * C) {
+                int c, mp;
+                if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
+                if constexpr (XCH == MODE_TMA_IN) {
+                    const T* re_pl = reinterpret_cast<const T*>(tile) + mp * C + c;
+                    const T* im_pl = re_pl + R * C;
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) { pre_r[i] = re_pl[i * M * C]; pre_i[i] = im_pl[i * M * C]; }
+                } else {
+                    const cx<T>* src = tile + c * R + mp;
+#pragma unroll
+                    for (int i = 0; i < R1; ++i) { const cx<T> v = src[i * M]; pre_r[i] = v.x; pre_i[i] = v.y; }
+                }
+            }
+            __syncthreads();     // the landing zone is free: stage 1 may overwrite it
         }
 
         // ---- stage 1: global -> registers -> (twiddle, DFT) -> tile (or global when S == 1) ------
@@ -500,6 +599,11 @@ template <typename T, class RL, int C, int NT, int KIND, int VARIANT = 0, int MI
 __global__ void __launch_bounds__(NT, MINB) fft_pass_kernel(const __grid_constant__ PassParams<T> p) {
     PassKernel<T, RL, C, NT, KIND, 0, VARIANT>::body(p, blockIdx.x);
 }
+// the same pass with an asynchronous tile input (MODE_TMA_IN / MODE_BULK_IN)
+template <typename T, class RL, int C, int NT, int KIND, int MODE, int VARIANT = 0, int MINB = 0>
+__global__ void __launch_bounds__(NT, MINB) fft_pass_async_kernel(const __grid_constant__ PassParams<T> p) {
+    PassKernel<T, RL, C, NT, KIND, MODE, VARIANT>::body(p, blockIdx.x);
+}
 
 // ---------------------------------------------------------------------------------------------
 // One HBM pass for transforms that fit the shared memory of a thread-block cluster (2^13..2^17 points): the K CTAs of a
@@ -519,43 +623,83 @@ __global__ void __launch_bounds__(NT, MINB) fft_cluster2_kernel(const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fused two-pass launch for signals that live in L2 (N <= 2^20): ONE cooperative grid runs the tiles
-// of pass 1, meets at a grid-wide barrier, then runs the tiles of pass 2.  At these sizes a pass is a
-// single latency-bound wave and a launch costs ~2.5 us of a ~10 us pass, so removing one launch (and
-// the drain/fill between the passes) is worth 10-30 %.
-// bar[0] = arrival count, bar[1] = generation; self-resetting, so CUDA-graph replays can reuse it.
+// Both passes of a two-pass plan in ONE persistent launch with the intermediates in an L2-resident ring.
+//
+// A two-launch plan writes the whole batch's intermediate to HBM and reads it back: 2x the compulsory traffic, which
+// caps it at half the roofline however good each pass is (round 1: 4096 x 2^16 f32 at 0.47 with both passes at
+// 0.92-0.96).  Here one grid runs both passes at once, its CTAs drawing pass-1 and pass-2 tiles from one ordered ticket queue.
+// Pass 1 of transform b writes slot b % ring of a workspace of `ring` transforms (sized to stay in the 126 MB L2, 24-32 MiB),
+// pass 2 of transform b reads it back while it is still in L2, and the slot is rewritten (or discarded) before its dirty
+// lines are evicted, so HBM sees the batch once in and once out (tools/dsmem_bench.cu `ring`: 5.4 TB/s of
+// compulsory traffic against 3.4 TB/s for the HBM round trip).  Dependencies are per-transform counters:
+//     a pass-2 tile of transform b waits for done1[b] == tiles1   (all of its rows have been produced)
+//     a pass-1 tile of transform b waits for done2[b - ring] == tiles2   (its slot has been drained)
+// released with red.release.gpu after a block barrier and acquired with ld.acquire.gpu by thread 0 before a block barrier.
+// With batch == 1 this is a fused two-pass launch of a lone transform (replaces round 1's cooperative-launch + grid-barrier
+// experiment).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nblocks) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        volatile unsigned* vgen = bar + 1;
-        const unsigned gen = *vgen;
-        const unsigned prev = atomicAdd(bar, 1u);
-        if (prev == nblocks - 1) {
-            bar[0] = 0;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*vgen == gen) __nanosleep(32);
-        }
-        __threadfence();
-    }
+struct PipeCtl {
+    unsigned* ticket;              // next work item (zeroed before the launch, like done1 / done2)
+    unsigned* done1;               // [batch] pass-1 tiles finished per transform
+    unsigned* done2;               // [batch] pass-2 tiles finished per transform
+    unsigned tiles1, tiles2;       // tiles per transform in pass 1 / pass 2
+    unsigned batch, ring, delay;   // ring: workspace slots (transforms), a power of two; pass 2 runs `delay` < ring transforms behind
+    int discard;                   // pass 2 tells L2 to drop its input lines once read (discard.global.L2): no write-back of the ring
+};
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void wait_count(const unsigned* p, unsigned want) {
+    if (threadIdx.x == 0)
+        while (ld_acquire_gpu(p) < want) __nanosleep(64);
     __syncthreads();
 }
 
+// One CTA = one tile.  The tile is NOT derived from blockIdx: the CTA draws a ticket when it starts running, so tickets are
+// held by resident CTAs only and every wait below is for a smaller ticket -- forward progress without assuming anything about
+// the order in which the hardware dispatches CTAs (the decoupled-look-back argument).  Ticket order:
+//     step s  =  [pass-1 tiles of transform s]  then  [pass-2 tiles of transform s - delay]
+// so pass 1 runs `delay` transforms ahead of pass 2 and both kinds of tile are in flight on every SM.  No loop around the
+// pass bodies: each keeps (about) the register allocation it has as a kernel of its own.
+template <class PK, typename T>
+__device__ __forceinline__ void pipe_discard_rows(const PassParams<T>& p, unsigned bq, unsigned kt) {
+    // this tile's input rows (C rows of R contiguous interleaved elements each) will not be read again: let L2 drop them
+    constexpr int LINES_PER_ROW = (int)(PK::R * sizeof(cx<T>) / 128);
+    const char* rows = reinterpret_cast<const char*>(reinterpret_cast<const cx<T>*>(p.in_re) + (long long)bq * p.in_bstride +
+                                                     (long long)kt * PK::TILE_C * PK::R);
+    for (int q = threadIdx.x; q < PK::TILE_C * LINES_PER_ROW; q += blockDim.x)
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(rows + (size_t)q * 128) : "memory");
+}
+
 template <class PK1, class PK2, typename T, int NTF, int MINB>
-__global__ void __launch_bounds__(NTF, MINB) fft_fused2_kernel(const __grid_constant__ PassParams<T> p1,
-                                                              const __grid_constant__ PassParams<T> p2,
-                                                              unsigned tiles1, unsigned tiles2, unsigned* bar) {
-    for (unsigned t = blockIdx.x; t < tiles1; t += gridDim.x) {
-        PK1::body(p1, t);
+__global__ void __launch_bounds__(NTF, MINB) fft_pipe2_kernel(const __grid_constant__ PassParams<T> p1,
+                                                             const __grid_constant__ PassParams<T> p2,
+                                                             const __grid_constant__ PipeCtl c) {
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(c.ticket, 1u);
+    __syncthreads();
+    const unsigned t = s_ticket;
+    const unsigned L = c.tiles1 + c.tiles2;
+    const unsigned step = t / L, j = t - step * L;
+    if (j < c.tiles1) {
+        if (step >= c.batch) return;
+        if (step >= c.ring) wait_count(c.done2 + (step - c.ring), c.tiles2);          // the slot has been drained
+        PK1::body(p1, step * c.tiles1 + j);
         __syncthreads();
-    }
-    grid_barrier(bar, gridDim.x);
-    for (unsigned t = blockIdx.x; t < tiles2; t += gridDim.x) {
-        PK2::body(p2, t);
+        if (threadIdx.x == 0) red_release_gpu(c.done1 + step, 1u);
+    } else {
+        if (step < c.delay || step - c.delay >= c.batch) return;
+        const unsigned b = step - c.delay, kt = j - c.tiles1;
+        wait_count(c.done1 + b, c.tiles1);                                             // all rows of the transform have been produced
+        PK2::body(p2, b * c.tiles2 + kt);
         __syncthreads();
+        if (c.discard) { pipe_discard_rows<PK2, T>(p2, b & (c.ring - 1), kt); __syncthreads(); }
+        if (threadIdx.x == 0) red_release_gpu(c.done2 + b, 1u);
     }
 }
 

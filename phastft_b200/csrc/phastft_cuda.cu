@@ -68,6 +68,38 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn tensor_map_encoder() {
+    static encode_tiled_fn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<encode_tiled_fn>(p);
+    }();
+    return fn;
+}
+// {cols (contiguous), rows (stride row_stride elements), batch (stride bstride elements)} of T; box {box_cols, box_rows, 1}
+template <typename T>
+bool encode_tile_map(CUtensorMap* map, const T* base, size_t cols, size_t rows, size_t row_stride, size_t batch, size_t bstride,
+                     unsigned box_cols, unsigned box_rows) {
+    encode_tiled_fn enc = tensor_map_encoder();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || ((row_stride * sizeof(T)) & 15) || ((bstride * sizeof(T)) & 15)) return false;
+    cuuint64_t dims[3] = {cols, rows, batch};
+    cuuint64_t strides[2] = {row_stride * sizeof(T), bstride * sizeof(T)};
+    if (batch == 1) strides[1] = strides[0] * rows;      // unused dimension: any legal stride
+    cuuint32_t box[3] = {box_cols, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return enc(map, dt, 3, const_cast<T*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // =================================================================================================
 // kernel registry (the kernels themselves are instantiated in reg_strided.cu / reg_row.cu / reg_multi.cu)
 // =================================================================================================
@@ -152,6 +184,8 @@ template <typename T>
 struct PassDesc {
     const KernelEntry<T>* k = nullptr;    // kernel for a lone transform
     const KernelEntry<T>* kb = nullptr;   // kernel when the call carries many transforms (multi-wave grids)
+    const KernelEntry<T>* kt = nullptr;   // 2-pass plans of lone transforms: the pass with an asynchronous (TMA) tile input
+    size_t tw_wc_off_t = (size_t)-1;      // W_L^(c*m) table for `kt`
     int log2R = 0, log2A = 0, log2B = 0, log2R1 = 0, log2Rprev = 0, has_tw = 0, tw_shift = 0;
     size_t tw_stage_off = 0;  // byte offsets into the table blob
     size_t tw_wc_off = (size_t)-1;
@@ -171,9 +205,12 @@ struct Plan {
     PassDesc<T> cl_pass[2];
     size_t cl_min_batch = 0;           // calls with at least this many transforms use the cluster launch
     int cl_max_active = 0;             // cudaOccupancyMaxActiveClusters of that launch on this device
-    const FusedEntry<T>* fused = nullptr;   // 2-pass plans: both passes in one cooperative launch (lone transforms)
-    int fused_grid = 0;
-    unsigned* fuse_bar = nullptr;      // grid barrier state {count, generation}
+    // 2-pass plans: both passes in one persistent launch, intermediates in an L2-resident ring (fft_pipe2_kernel)
+    const PipeEntry<T>* pipe_b = nullptr;   // for batched calls (pairs pass[0].kb / pass[1].kb)
+    const PipeEntry<T>* pipe_1 = nullptr;   // for a lone transform (pairs pass[0].k / pass[1].k); off unless PHASTFT_PIPE_LONE=1
+    int pipe_grid_b = 0, pipe_grid_1 = 0;   // co-resident CTAs of those launches on this device
+    mutable unsigned char* pipe_state = nullptr;   // ticket + done1[batch] + done2[batch], zeroed per call
+    mutable size_t pipe_state_batch = 0;
     // table blob: [tw2_hi][tw2_lo][per pass W_R][wc]
     std::vector<unsigned char> blob_host;
     unsigned char* blob_dev = nullptr;
@@ -205,7 +242,7 @@ struct Plan {
         DeviceGuard g(device);
         if (blob_dev) cudaFree(blob_dev);
         if (ws_re) cudaFree(ws_re);
-        if (fuse_bar) cudaFree(fuse_bar);
+        if (pipe_state) cudaFree(pipe_state);
         if (ws2_re) cudaFree(ws2_re);
         if (ws2_im) cudaFree(ws2_im);
         if (stage_re) cudaFree(stage_re);
@@ -220,7 +257,7 @@ struct Plan {
 // Layout of the intermediates between passes: planar (two halves of the workspace) or interleaved
 // complex.  Interleaved makes every access a 16-byte (f64) element, so a 64-byte run needs half as many
 // columns: the 1024-row middle tile of 2^25..2^26 shrinks from 128 KB to 64 KB and two CTAs share an SM
-// (2^26 f64 middle pass 646 -> 513 us, tools/tune25.py); streaming passes gain 2-9 % (tune24/25), single
+// (2^26 f64 middle pass 646 -> 513 us, profiles/r01_tune25*.txt); streaming passes gain 2-9 % (tune24/25), single
 // L2-resident transforms lose 2-7 %, hence the automatic rule.  PHASTFT_WS_IL=0|1 forces a layout.
 inline int ws_interleaved_mode() {
     const char* e = getenv("PHASTFT_WS_IL");
@@ -264,14 +301,14 @@ std::vector<int> choose_factors(int n) {
             pos = end + 1;
         }
     }
-    // A lone transform is one CTA only while that beats two many-CTA passes (tools/tune17.py: f64 2^12
+    // A lone transform is one CTA only while that beats two many-CTA passes (profiles/r01_tune17*.txt: f64 2^12
     // 7.9 us in one CTA vs 4.9 us as {6,6}; f32 2^12 5.6 vs 5.9 us).  Batches of <= 2^12-point transforms
     // always use the one-CTA kernel (Plan::alt_row): one launch, one HBM round trip.
     const int single_max = sizeof(T) == 8 ? 10 : 12;
     if (n <= single_max) return {n};
     // two passes while both tiles stay <= 1024 points long; the ends of a 3-pass plan are kept at
     // 2^8 so they can use 128-byte runs in a 64 KB tile, the middle pass takes the rest (<= 2^10)
-    // measured-best splits (tools/tune7.py, profiles/r01_tuning.md)
+    // measured-best splits (profiles/r01_tune7*.txt, profiles/r01_tuning.md)
     if (n <= 16) { int a = n / 2; return {a, n - a}; }
     if (n <= 20) { int a = (n + 1) / 2; return {a, n - a}; }
     if (n <= 22) return {7, n - 14, 7};
@@ -281,7 +318,7 @@ std::vector<int> choose_factors(int n) {
 }
 
 // `l2_resident`: the whole signal fits L2 (a few MiB .. 64 MiB).  There the passes are launch- and
-// latency-bound single waves and the tile width is chosen by a wave model (tools/tune15.py, tune16.py:
+// latency-bound single waves and the tile width is chosen by a wave model (profiles/r01_tune15*.txt, r01_tune16:
 // 2^18 f64 8.8 us with 4-column tiles vs 12.2 us with 8; 2^20 f32 16.6 us with 8 columns vs 25.4 us
 // with 16; 2^20 f64 stays at 8 columns because its 1024-row tile holds only one CTA per SM).
 template <typename T>
@@ -311,7 +348,7 @@ const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bo
     const KernelEntry<T>* best = nullptr;
     int best_rank = 1 << 30;
     for (const auto& e : registry<T>()) {
-        if (e.kind != kind || e.R != R) continue;
+        if (e.kind != kind || e.R != R || e.mode != MODE_PLAIN) continue;
         if (kind != KIND_ROW && e.C > max_c) continue;
         if (e.variant != want_variant) continue;
         int rank;
@@ -336,12 +373,12 @@ const KernelEntry<T>* pick_kernel(int kind, int R, int max_c, int pass_index, bo
     }
     if (!best && want_variant != 0) {   // requested variant does not exist for this tile: fall back to the default
         for (const auto& e : registry<T>())
-            if (e.kind == kind && e.R == R && e.variant == 0 && (kind == KIND_ROW || e.C <= max_c) && !best) best = &e;
+            if (e.kind == kind && e.R == R && e.variant == 0 && e.mode == MODE_PLAIN && (kind == KIND_ROW || e.C <= max_c) && !best) best = &e;
     }
     return best;
 }
 
-// One-CTA kernels: for a batch the radix-16 builds win at some sizes (tools/tune19.py: 2^8 6.7 vs 4.5 TB/s,
+// One-CTA kernels: for a batch the radix-16 builds win at some sizes (profiles/r01_tune19*.txt: 2^8 6.7 vs 4.5 TB/s,
 // f32 2^11 3.4 vs 2.2 TB/s, f64 2^11/2^12 3.4 vs 2.9 TB/s) while a lone transform prefers the default.
 template <typename T>
 const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
@@ -350,7 +387,7 @@ const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
         for (const auto& e : registry<T>())
             if (e.kind == KIND_ROW && e.R == R && e.variant == want) return &e;
     }
-    // measured per size (tools/tune19.py, tools/tune29.py); 0 = the lone-transform kernel is also the best batch kernel
+    // measured per size (profiles/r01_tune19*.txt, profiles/r01_tune29*.txt); 0 = the lone-transform kernel is also the best batch kernel
     const bool f64 = sizeof(T) == 8;
     int want = 0;
     switch (R) {
@@ -415,7 +452,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const bool wide = (p == 0 || last) && big;
         // interleaved 1024-row middle pass: half-width (64-byte-run) tile, two CTAs per SM
         const bool half_mid = il3 && p == 1 && f[p] == 10;
-        // lone 2^11-point f32 transform in one CTA: 8x16x16 (3.7 us) beats 4x8x8x8 (4.4 us), tools/tune30.py
+        // lone 2^11-point f32 transform in one CTA: 8x16x16 (3.7 us) beats 4x8x8x8 (4.4 us), profiles/r01_tune30*.txt
         const bool row2048_f32 = kind == KIND_ROW && f[p] == 11 && sizeof(T) == 4;
         const int pref_c = half_mid ? TileC<T>::CH : 0, pref_v = half_mid ? 62 : row2048_f32 ? 70 : 0;
         d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide, /*l2_resident=*/!big, /*rows_total=*/n >> f[p], pref_c, pref_v);
@@ -444,10 +481,34 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         }
         off = (off + 255) & ~size_t(255);
     }
+    // Lone transforms as two passes of asynchronous-input kernels (TMA boxes of the planar input into 64 KB tiles,
+    // interleaved intermediates, programmatic dependent launch): PHASTFT_TMA=0 disables, PHASTFT_TMA_VARIANT picks a build.
+    if (pl->num_passes == 2) {
+        int enabled = 0, want = 300;      // measured equal-or-slower than the plain kernels (profiles/r02_exp_tma1.txt): opt-in
+        if (const char* env = getenv("PHASTFT_TMA")) enabled = atoi(env);
+        if (getenv("PHASTFT_TMA_VARIANT") && !getenv("PHASTFT_TMA")) enabled = 1;
+        if (const char* env = getenv("PHASTFT_TMA_VARIANT")) want = atoi(env);
+        const KernelEntry<T>* t0 = nullptr; const KernelEntry<T>* t1 = nullptr;
+        if (enabled && tensor_map_encoder())
+            for (const auto& e : registry<T>()) {
+                if (e.variant != want) continue;
+                if (e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.R == (1 << f[0]) && e.C <= (1 << f[1])) t0 = &e;
+                if (e.mode == MODE_BULK_IN && e.kind == KIND_TRANS && e.R == (1 << f[1]) && e.C <= (1 << f[0])) t1 = &e;
+            }
+        if (t0 && t1) {
+            pl->pass[0].kt = t0; pl->pass[1].kt = t1;
+            PassDesc<T>& d = pl->pass[1];
+            d.tw_wc_off_t = off;
+            off += (size_t)t1->C * ((size_t(1) << f[1]) / t1->first_radix) * sizeof(cx<T>);
+            off = (off + 255) & ~size_t(255);
+        }
+    }
     // Batches of transforms that one CTA can hold (128 KB tile: 2^13 f64, 2^14 f32) use a one-CTA kernel: one launch,
     // one HBM round trip.  PHASTFT_ONE_CTA_MAX (log2) lowers the limit for re-tuning.
-    int one_cta_max = sizeof(T) == 8 ? 13 : 14;
-    if (const char* env = getenv("PHASTFT_ONE_CTA_MAX")) one_cta_max = atoi(env);
+    // 2^13 f64 / 2^14 f32 in one CTA (128 KB tile, one CTA per SM) measured slower than two passes of small tiles
+    // (205 vs 182 us and 159 vs 97 us per 2^24 points, profiles/r02_exp_cluster1.txt), so the default limit stays 2^12.
+    int one_cta_max = 12;
+    if (const char* env = getenv("PHASTFT_ONE_CTA_MAX")) one_cta_max = std::min(atoi(env), sizeof(T) == 8 ? 13 : 14);
     if (pl->num_passes >= 2 && ln <= one_cta_max) {
         PassDesc<T>& d = pl->alt_row;
         d.log2R = ln; d.log2A = 0; d.log2B = 0; d.log2R1 = ln;
@@ -464,9 +525,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
     // cluster launch.  PHASTFT_CLUSTER=0 disables, PHASTFT_CLUSTER_VARIANT=<id> picks a build, PHASTFT_CLUSTER_MIN_BATCH
     // sets the smallest call that uses it (a lone transform keeps K SMs busy, the two-launch plan the whole chip).
     {
-        int want = 0, enabled = 1;
+        int want = 0, enabled = 0;        // measured slower than the two-launch plan at every size (profiles/r02_exp_cluster1.txt): opt-in
         if (const char* env = getenv("PHASTFT_CLUSTER")) enabled = atoi(env);
-        if (const char* env = getenv("PHASTFT_CLUSTER_VARIANT")) want = atoi(env);
+        if (const char* env = getenv("PHASTFT_CLUSTER_VARIANT")) { want = atoi(env); if (!getenv("PHASTFT_CLUSTER")) enabled = 1; }
+        if (getenv("PHASTFT_CLUSTER_MIN_BATCH") && !getenv("PHASTFT_CLUSTER")) enabled = 1;
         if (enabled && !pl->alt_row.k)
             for (const auto& ce : cluster_registry<T>())
                 if (ce.log2n == ln && ce.variant == want) { pl->cl = &ce; break; }
@@ -505,10 +567,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             root_of_unity(e, R, re, im);
             tw[e].x = (T)re; tw[e].y = (T)im;
         }
-        for (int which = 0; which < 2; ++which) {
-            const KernelEntry<T>* kk = which ? d.kb : d.k;
-            const size_t woff = which ? d.tw_wc_off_b : d.tw_wc_off;
-            if (woff == (size_t)-1 || (which && woff == d.tw_wc_off)) continue;
+        for (int which = 0; which < 3; ++which) {
+            const KernelEntry<T>* kk = which == 2 ? d.kt : which ? d.kb : d.k;
+            const size_t woff = which == 2 ? d.tw_wc_off_t : which ? d.tw_wc_off_b : d.tw_wc_off;
+            if (!kk || woff == (size_t)-1 || (which == 1 && woff == d.tw_wc_off)) continue;
             // W_L^(c*m), L = N (2-pass plan), [c][m] layout, m < M = R / first_radix
             const size_t M = R / kk->first_radix;
             cx<T>* wc = reinterpret_cast<cx<T>*>(pl->blob_host.data() + woff);
@@ -531,6 +593,8 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].k->smem));
         if (pl->pass[p].kb)
             CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kb->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kb->smem));
+        if (pl->pass[p].kt)
+            CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kt->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kt->smem));
     }
     if (pl->alt_row.k)
         CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.k->smem));
@@ -573,26 +637,30 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         }
     }
     if (pl->num_passes == 2) {
-        // measured slower than two plain launches (tools/tune21.py: 2^20 f64 23.6 vs 21.1 us, 2^16 8.8 vs 7.8 us):
-        // the cooperative launch and the grid barrier cost more than the launch they save.  Off by default.
-        static const bool use_fuse = [] { const char* e = getenv("PHASTFT_FUSE"); return e ? atoi(e) != 0 : false; }();
-        const KernelEntry<T>* a = pl->pass[0].k; const KernelEntry<T>* b = pl->pass[1].k;
-        if (use_fuse)
-            for (const auto& fe : fused_registry<T>())
-                if (fe.R1 == a->R && fe.C1 == a->C && fe.NT1 == a->NT && fe.rad1 == a->radices && fe.R2 == b->R && fe.C2 == b->C &&
-                    fe.NT2 == b->NT && fe.rad2 == b->radices) { pl->fused = &fe; break; }
-        if (pl->fused) {
-            int occ = 0, sms = 0, coop = 0;
-            CUDA_TRY(cudaFuncSetAttribute(pl->fused->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fused->smem));
-            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-            CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pl->fused->fn, pl->fused->NT, pl->fused->smem));
-            const size_t tiles = std::max((n >> f[0]) / a->C, (n >> f[1]) / b->C);
-            pl->fused_grid = (int)std::min<size_t>(tiles, (size_t)sms * std::max(occ, 0));
-            if (!coop || occ < 1 || pl->fused_grid < 1) pl->fused = nullptr;
-            else {
-                CUDA_TRY(cudaMalloc(&pl->fuse_bar, 2 * sizeof(unsigned)));
-                CUDA_TRY(cudaMemset(pl->fuse_bar, 0, 2 * sizeof(unsigned)));
+        // PHASTFT_PIPE=0 disables the pipelined launch; PHASTFT_PIPE_LONE=1 also sends lone transforms through it
+        int enabled = 0, lone = 0;        // opt-in until it beats two launches (profiles/r02_exp_pipe_kernel_v*.txt)
+        if (const char* e = getenv("PHASTFT_PIPE")) enabled = atoi(e);
+        if (const char* e = getenv("PHASTFT_PIPE_LONE")) lone = atoi(e);
+        auto find = [&](const KernelEntry<T>* a, const KernelEntry<T>* b) -> const PipeEntry<T>* {
+            if (!a || !b) return nullptr;
+            for (const auto& pe : pipe_registry<T>())
+                if (pe.R1 == a->R && pe.C1 == a->C && pe.NT1 == a->NT && pe.rad1 == a->radices && pe.R2 == b->R && pe.C2 == b->C &&
+                    pe.NT2 == b->NT && pe.rad2 == b->radices) return &pe;
+            return nullptr;
+        };
+        auto resident = [&](const PipeEntry<T>* pe) -> int {
+            int occ = 0, sms = 0;
+            if (cudaFuncSetAttribute(pe->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pe->smem) != cudaSuccess ||
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pe->fn, pe->NT, pe->smem) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+            return sms * std::max(occ, 0);
+        };
+        if (enabled) {
+            pl->pipe_b = find(pl->pass[0].kb, pl->pass[1].kb);
+            if (pl->pipe_b && (pl->pipe_grid_b = resident(pl->pipe_b)) < 2) pl->pipe_b = nullptr;
+            if (lone) {
+                pl->pipe_1 = find(pl->pass[0].k, pl->pass[1].k);
+                if (pl->pipe_1 && (pl->pipe_grid_1 = resident(pl->pipe_1)) < 2) pl->pipe_1 = nullptr;
             }
         }
     }
@@ -604,6 +672,14 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             const auto* k = pl->pass[p].k;
             s += std::string(p ? " |" : "") + " " + kind_name(k->kind) + " R=" + std::to_string(k->R) + "(" + k->radices + ") C=" +
                  std::to_string(k->C) + " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
+        }
+        if (pl->num_passes == 2 && pl->pass[0].kt) {
+            s += " || lone planar: ";
+            for (int p = 0; p < 2; ++p) {
+                const auto* k = pl->pass[p].kt;
+                s += std::string(p ? " | " : "") + kind_name(k->kind) + " R=" + std::to_string(k->R) + "(" + k->radices + ") C=" + std::to_string(k->C) +
+                     " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
+            }
         }
         if (pl->l2_group) s += " | L2-blocked tail: " + std::to_string(pl->l2_group) + " k1/group";
         bool differs = false;
@@ -617,7 +693,8 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             }
         }
         if (pl->num_passes >= 2) s += pl->ws_il == 1 ? " [interleaved intermediates]" : pl->ws_il == 0 ? " [planar intermediates]" : "";
-        if (pl->fused) s += " [fused launch, grid " + std::to_string(pl->fused_grid) + "]";
+        if (pl->pipe_b) s += " [batches: one pipelined launch, " + std::to_string(pl->pipe_grid_b) + " resident CTAs, L2 ring]";
+        if (pl->pipe_1) s += " [lone: one pipelined launch, " + std::to_string(pl->pipe_grid_1) + " resident CTAs]";
         if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
         if (pl->cl)
             s += " || batches >= " + std::to_string(pl->cl_min_batch) + ": CLUSTER K=" + std::to_string(pl->cl->K) + " NT=" + std::to_string(pl->cl->NT) +
@@ -655,18 +732,30 @@ struct Io {
 // whose first-pass output digit k1 lies in [k1_lo, k1_lo + k1_cnt) -- the unit of L2 blocking.
 template <typename T>
 int32_t prepare_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, long long k1_lo, long long k1_cnt,
-                     PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out);
+                     PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out, bool use_kt = false);
 
+// use_kt: launch the pass's asynchronous-input kernel (PassDesc::kt); the caller has checked its preconditions
+// (pass 0: planar 16-byte-aligned input; last pass: interleaved workspace).
 template <typename T>
 int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, cudaStream_t stream,
-                    long long k1_lo = 0, long long k1_cnt = -1) {
+                    long long k1_lo = 0, long long k1_cnt = -1, bool use_kt = false) {
     PassParams<T> prm;
     const KernelEntry<T>* k = nullptr;
     unsigned long long blocks = 0;
-    int32_t st = prepare_pass(pl, p, base, batch, k1_lo, k1_cnt, prm, k, blocks);
+    int32_t st = prepare_pass(pl, p, base, batch, k1_lo, k1_cnt, prm, k, blocks, use_kt);
     if (st) return st;
+    if (k->mode == MODE_TMA_IN) {
+        const size_t B = size_t(1) << prm.log2B;
+        const unsigned box_rows = (unsigned)std::min(k->R, 256);
+        if (!encode_tile_map<T>(&prm.tmap_re, prm.in_re, B, (size_t)k->R, B, batch, (size_t)prm.in_bstride, (unsigned)k->C, box_rows) ||
+            !encode_tile_map<T>(&prm.tmap_im, prm.in_im, B, (size_t)k->R, B, batch, (size_t)prm.in_bstride, (unsigned)k->C, box_rows))
+            return fail(PHASTFT_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    }
     void* args[] = {&prm};
-    static const bool use_pdl = [] { const char* e = getenv("PHASTFT_PDL"); return e ? atoi(e) != 0 : false; }();   // measured: no gain at 2^20, -10% at 2^24+ (tune8)
+    // Programmatic dependent launch: measured no gain with 128 KB tiles (the next grid cannot become resident early), -10%
+    // at 2^24+, and slower too with the 64 KB asynchronous-input tiles (profiles/r02_exp_tma1.txt).  PHASTFT_PDL=1 enables it.
+    static const int pdl_env = [] { const char* e = getenv("PHASTFT_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+    const bool use_pdl = pdl_env > 0;     // off by default: measured slower with and without the asynchronous-input kernels
     if (use_pdl) {
         // Programmatic dependent launch: back-to-back passes overlap the next grid's launch and prologue
         // with the previous grid's tail (the kernel waits with griddepcontrol.wait before its first access).
@@ -688,20 +777,22 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
 
 template <typename T>
 int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const PassParams<T>& base, size_t batch, long long k1_lo,
-                          long long k1_cnt, PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out);
+                          long long k1_cnt, PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out,
+                          bool use_kt = false);
 
 template <typename T>
 int32_t prepare_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t batch, long long k1_lo, long long k1_cnt,
-                     PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out) {
+                     PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out, bool use_kt) {
     const PassDesc<T>& d = (p == ALT_ROW_PASS) ? pl.alt_row : pl.pass[p];
-    return prepare_pass_desc(pl, d, p, base, batch, k1_lo, k1_cnt, prm_out, k_out, blocks_out);
+    return prepare_pass_desc(pl, d, p, base, batch, k1_lo, k1_cnt, prm_out, k_out, blocks_out, use_kt);
 }
 
 template <typename T>
 int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const PassParams<T>& base, size_t batch, long long k1_lo,
-                          long long k1_cnt, PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out) {
-    const bool many = d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
-    const KernelEntry<T>* k = many ? d.kb : d.k;
+                          long long k1_cnt, PassParams<T>& prm_out, const KernelEntry<T>*& k_out, unsigned long long& blocks_out,
+                          bool use_kt) {
+    const bool many = !use_kt && d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
+    const KernelEntry<T>* k = use_kt ? d.kt : many ? d.kb : d.k;
     PassParams<T> prm = base;
     prm.batch = (int)batch;
     prm.log2A = d.log2A; prm.log2B = d.log2B; prm.log2R1 = d.log2R1; prm.log2Rprev = d.log2Rprev;
@@ -710,7 +801,7 @@ int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const 
     prm.tw2.lo = reinterpret_cast<const double2*>(pl.blob_dev + pl.lo_off);
     prm.tw2.lo_bits = pl.lo_bits;
     prm.tw_stage = reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_stage_off);
-    const size_t wc_off = many ? d.tw_wc_off_b : d.tw_wc_off;
+    const size_t wc_off = use_kt ? d.tw_wc_off_t : many ? d.tw_wc_off_b : d.tw_wc_off;
     prm.tw_wc = wc_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + wc_off);
     unsigned long long blocks;
     prm.blk_offset = 0; prm.kt_base = 0; prm.log2_ktn = d.log2R1 - ilog2(k->C);
@@ -732,7 +823,7 @@ int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const 
     return PHASTFT_OK;
 }
 
-// A batch is processed in chunks so the workspace stays bounded.  Measured on B200 (tools/tune12.py):
+// A batch is processed in chunks so the workspace stays bounded.  Measured on B200 (profiles/r01_tune12*.txt):
 // keeping a chunk's intermediate L2-resident (48 MiB chunks) is SLOWER than few large launches --
 // 4096 x 2^16 f32: 1.88 ms at 48 MiB, 1.61 ms at 192 MiB, 1.50 ms unchunked -- so the default chunk is
 // as large as the workspace cap allows (PHASTFT_L2_CHUNK_MB overrides).
@@ -745,6 +836,25 @@ inline size_t l2_chunk_bytes() {
     return v;
 }
 
+// Ring of workspace slots of the pipelined two-pass launch: the largest power-of-two number of transforms whose
+// intermediates fit PHASTFT_PIPE_RING_MB (default 32 MiB: tools/dsmem_bench.cu `ring` keeps 5.4 TB/s up to 32-48 MiB and
+// falls to the HBM round trip's 3.4 TB/s at 96 MiB), at least 1.
+inline size_t pipe_ring_bytes() {
+    static const size_t v = [] {
+        long mb = 32;
+        if (const char* env = getenv("PHASTFT_PIPE_RING_MB")) mb = atol(env);
+        return (size_t)std::max(1L, mb) << 20;
+    }();
+    return v;
+}
+template <typename T>
+size_t pipe_ring_transforms(const Plan<T>& pl, size_t batch) {
+    const size_t bytes_per = pl.n * 2 * sizeof(T);
+    size_t ring = 1;
+    while (ring * 2 * bytes_per <= pipe_ring_bytes() && ring * 2 <= batch) ring *= 2;
+    if (ring < 2 && batch > 1) ring = 2;            // two slots at least: pass 1 of b+1 beside pass 2 of b
+    return ring;
+}
 // caller holds pl.mu
 template <typename T>
 int32_t grow_workspace(const Plan<T>& pl, size_t transforms, cudaStream_t stream) {
@@ -768,6 +878,7 @@ int32_t plan_reserve(const Plan<T>* pl, size_t batch) {
     const size_t bytes_per = pl->n * 2 * sizeof(T);
     size_t chunk = std::max<size_t>(1, l2_chunk_bytes() / bytes_per);
     chunk = std::min(chunk, batch);
+    if (pl->pipe_b && (batch << pl->log2n) >= (size_t(1) << 21)) chunk = pipe_ring_transforms(*pl, batch);
     return grow_workspace(*pl, chunk, nullptr);
 }
 
@@ -855,6 +966,15 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     size_t chunk = std::max<size_t>(1, l2_chunk_bytes() / bytes_per);
     chunk = std::min(chunk, batch);
     if (pl.num_passes == 3 && pl.ws2_re != nullptr) chunk = 1;
+    // pipelined two-pass launch (see fft_pipe2_kernel): the workspace is a ring of transforms instead of the whole chunk
+    const PipeEntry<T>* pipe = nullptr;
+    if (pl.num_passes == 2 && !pass_events) {
+        if (batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21)) pipe = pl.pipe_b;
+        else if (batch == 1 && io.in_il == 0 && io.out_il == 0) pipe = pl.pipe_1;
+    }
+    size_t ws_need = chunk;
+    const size_t ring = pipe ? pipe_ring_transforms(pl, batch) : 0;
+    if (pipe) ws_need = ring;
     // Workspace reuse is ordered by the stream itself when consecutive calls use the same stream;
     // a call on a different stream first waits for the previous user.  While `stream` is being
     // captured into a CUDA graph the cross-stream bookkeeping is skipped (the graph's owner orders
@@ -862,39 +982,61 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(stream, &cap));
     const bool capturing = cap != cudaStreamCaptureStatusNone;
-    if (pl.ws_elems < chunk * pl.n) {
+    if (pl.ws_elems < ws_need * pl.n || (pipe && pl.pipe_state_batch < batch)) {
         // The plan is created with room for one transform; the first batched call grows it (synchronising).
         // phastft_plan_dit_*_reserve(batch) does this ahead of time; inside a graph capture growing is an error.
         if (capturing)
             return fail(PHASTFT_ERR_INVALID_ARG, "the plan's workspace is too small for this batch and the stream is being captured: "
                                                  "call phastft_plan_dit_*_reserve(batch) before capturing");
-        int32_t st = grow_workspace(pl, chunk, stream);
+        int32_t st = grow_workspace(pl, ws_need, stream);
         if (st) return st;
+        if (pipe && pl.pipe_state_batch < batch) {
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (pl.pipe_state) cudaFree(pl.pipe_state);
+            pl.pipe_state = nullptr; pl.pipe_state_batch = 0;
+            const size_t cap = std::max<size_t>(batch, 4096);
+            CUDA_TRY(cudaMalloc(&pl.pipe_state, 64 + 2 * cap * sizeof(unsigned)));
+            pl.pipe_state_batch = cap;
+        }
     }
     if (!capturing && pl.ws_last_stream != stream && pl.ws_used) CUDA_TRY(cudaStreamWaitEvent(stream, pl.ws_free, 0));
     const int P = pl.num_passes;
-    if (P == 2 && pl.fused && batch == 1 && !pass_events) {
+    if (pipe) {
+        const bool lone = batch == 1;
+        const int il_p = lone ? (pl.ws_il >= 0 ? pl.ws_il : 0) : (pl.ws_il >= 0 ? pl.ws_il : 1);
         PassParams<T> b1, b2, p1, p2;
         memset(&b1, 0, sizeof(b1)); memset(&b2, 0, sizeof(b2));
         b1.scale = T(1);
         b1.in_re = io.in_re; b1.in_im = io.in_im; b1.in_bstride = io.in_bstride; b1.in_interleaved = io.in_il;
-        b1.out_re = pl.ws_re; b1.out_im = pl.ws_im; b1.out_bstride = (long long)pl.n;
-        b2.in_re = pl.ws_re; b2.in_im = pl.ws_im; b2.in_bstride = (long long)pl.n;
+        b1.out_re = pl.ws_re; b1.out_im = pl.ws_re + ring * pl.n; b1.out_bstride = (long long)pl.n; b1.out_interleaved = il_p;
+        b1.out_ring = (int)ring;
+        b2.in_re = pl.ws_re; b2.in_im = pl.ws_re + ring * pl.n; b2.in_bstride = (long long)pl.n; b2.in_interleaved = il_p;
+        b2.in_ring = (int)ring;
         b2.out_re = io.out_re; b2.out_im = io.out_im; b2.out_bstride = io.out_bstride; b2.out_interleaved = io.out_il;
         b2.scale = scale;
         const KernelEntry<T>* k1 = nullptr; const KernelEntry<T>* k2 = nullptr;
         unsigned long long t1 = 0, t2 = 0;
-        int32_t st = prepare_pass(pl, 0, b1, 1, 0, -1, p1, k1, t1);
-        if (!st) st = prepare_pass(pl, 1, b2, 1, 0, -1, p2, k2, t2);
+        // descriptors with the batch flavour of each pass's kernel (prepare_pass picks kb for many-transform calls)
+        int32_t st = prepare_pass(pl, 0, b1, batch, 0, -1, p1, k1, t1);
+        if (!st) st = prepare_pass(pl, 1, b2, batch, 0, -1, p2, k2, t2);
         if (st) return st;
-        unsigned tiles1 = (unsigned)t1, tiles2 = (unsigned)t2;
-        unsigned* bar = pl.fuse_bar;
-        void* args[] = {&p1, &p2, &tiles1, &tiles2, &bar};
-        static const int fuse_mode = [] { const char* e = getenv("PHASTFT_FUSE"); return e ? atoi(e) : 0; }();
-        if (fuse_mode == 2)   // plain launch: the grid is sized to be co-resident, so the barrier cannot deadlock in practice
-            CUDA_TRY(cudaLaunchKernel(pl.fused->fn, dim3((unsigned)pl.fused_grid), dim3(pl.fused->NT), args, pl.fused->smem, stream));
-        else
-            CUDA_TRY(cudaLaunchCooperativeKernel(pl.fused->fn, dim3((unsigned)pl.fused_grid), dim3(pl.fused->NT), args, pl.fused->smem, stream));
+        if (k1->R != pipe->R1 || k1->C != pipe->C1 || k2->R != pipe->R2 || k2->C != pipe->C2)
+            return fail(PHASTFT_ERR_INVALID_ARG, "pipelined launch: kernel pair does not match the plan");
+        PipeCtl ctl;
+        ctl.ticket = reinterpret_cast<unsigned*>(pl.pipe_state);
+        ctl.done1 = reinterpret_cast<unsigned*>(pl.pipe_state + 64);
+        ctl.done2 = ctl.done1 + pl.pipe_state_batch;
+        ctl.tiles1 = (unsigned)(t1 / batch); ctl.tiles2 = (unsigned)(t2 / batch);
+        ctl.batch = (unsigned)batch; ctl.ring = (unsigned)ring;
+        ctl.delay = lone ? 1u : (unsigned)std::max<size_t>(1, ring / 2);
+        static const int discard_env = [] { const char* e = getenv("PHASTFT_PIPE_DISCARD"); return e ? atoi(e) : 1; }();
+        ctl.discard = (discard_env && il_p == 1 && !lone) ? 1 : 0;
+        CUDA_TRY(cudaMemsetAsync(pl.pipe_state, 0, 64 + 2 * pl.pipe_state_batch * sizeof(unsigned), stream));
+        const unsigned long long items = (unsigned long long)(batch + ctl.delay) * (ctl.tiles1 + ctl.tiles2);
+        if (items > 0x7fffffffULL) return fail(PHASTFT_ERR_INVALID_ARG, "grid too large");
+        const unsigned grid = (unsigned)items;                               // one CTA per work item (a ticket decides which)
+        void* args[] = {&p1, &p2, &ctl};
+        CUDA_TRY(cudaLaunchKernel(pipe->fn, dim3(grid), dim3(pipe->NT), args, pipe->smem, stream));
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (!capturing) {
             CUDA_TRY(cudaEventRecord(pl.ws_free, stream));
@@ -948,7 +1090,11 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
         return PHASTFT_OK;
     }
     const bool many_call = batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
-    const int il = pl.ws_il >= 0 ? pl.ws_il : ((P == 3 || many_call) ? 1 : 0);
+    // asynchronous-input kernels: planar 16-byte-aligned input whose batch stride keeps the alignment, interleaved intermediates
+    const bool tma = P == 2 && pl.pass[0].kt && pl.pass[1].kt && !many_call && io.in_il == 0 && pl.ws_il != 0 &&
+                     ((reinterpret_cast<uintptr_t>(io.in_re) | reinterpret_cast<uintptr_t>(io.in_im)) & 15) == 0 &&
+                     (batch == 1 || ((size_t)io.in_bstride * sizeof(T)) % 16 == 0);
+    const int il = tma ? 1 : pl.ws_il >= 0 ? pl.ws_il : ((P == 3 || many_call) ? 1 : 0);
     for (size_t done = 0; done < batch; done += chunk) {
         const size_t nb = std::min(chunk, batch - done);
         for (int p = 0; p < P; ++p) {
@@ -974,7 +1120,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
                 prm.out_interleaved = il;
             }
             if (pass_events && done == 0 && p == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
-            int32_t st = launch_pass(pl, p, prm, nb, stream);
+            int32_t st = launch_pass(pl, p, prm, nb, stream, 0, -1, tma);
             if (st) return st;
             if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[p + 1], stream));
         }

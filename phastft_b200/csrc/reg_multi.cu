@@ -1,6 +1,6 @@
 // reg_multi.cu -- instantiates the launches that run BOTH passes of a two-pass plan:
 //   fft_cluster2_kernel  a K-CTA thread-block cluster per transform, intermediate through distributed shared memory
-//   fft_fused2_kernel    one co-resident grid per lone L2-resident transform, intermediate through L2, grid barrier
+//   fft_pipe2_kernel     one persistent grid per call, intermediates in an L2-resident ring, per-transform counters
 // Compiled per precision: -DPHAST_T=double|float.
 #include "registry.h"
 
@@ -42,15 +42,15 @@ ClusterEntry<T> make_cluster() {
     return e;
 }
 
-template <typename T, class RL1, int C1, int NT1, int V1, class RL2, int C2, int NT2, int V2>
-FusedEntry<T> make_fused() {
+template <typename T, class RL1, int C1, int NT1, int V1, class RL2, int C2, int NT2, int V2, int MINB>
+PipeEntry<T> make_pipe() {
     using PK1 = PassKernel<T, RL1, C1, NT1, KIND_COL, 0, V1>;
     using PK2 = PassKernel<T, RL2, C2, NT2, KIND_TRANS, 0, V2>;
     constexpr int NTF = NT1 > NT2 ? NT1 : NT2;
-    FusedEntry<T> e;
+    PipeEntry<T> e;
     e.R1 = RL1::R(); e.C1 = C1; e.NT1 = NT1; e.R2 = RL2::R(); e.C2 = C2; e.NT2 = NT2;
     e.rad1 = radix_string<RL1>(); e.rad2 = radix_string<RL2>();
-    e.fn = reinterpret_cast<const void*>(&fft_fused2_kernel<PK1, PK2, T, NTF, 1>);
+    e.fn = reinterpret_cast<const void*>(&fft_pipe2_kernel<PK1, PK2, T, NTF, MINB>);
     e.NT = NTF;
     e.smem = PK1::SMEM_BYTES > PK2::SMEM_BYTES ? PK1::SMEM_BYTES : PK2::SMEM_BYTES;
     return e;
@@ -90,38 +90,31 @@ const std::vector<ClusterEntry<PHAST_T>>& cluster_registry<PHAST_T>() {
     return reg;
 }
 
-// Fused two-pass launches: the pairs are exactly the default 2-pass plans 2^11..2^20; the knob values (V) repeat the
-// ones of the default registry entries so fused and unfused results are bit-identical.
+// Pipelined two-pass launches.  The pairs are the plans the planner makes for BATCHES of 2^13..2^20-point transforms
+// (PassDesc::kb: 64-byte-run tiles) and for a lone 2^20; the knob values (V) repeat the ones of the registry entries so
+// pipelined and two-launch results are bit-identical.
 template <>
-const std::vector<FusedEntry<PHAST_T>>& fused_registry<PHAST_T>() {
+const std::vector<PipeEntry<PHAST_T>>& pipe_registry<PHAST_T>() {
     using T = PHAST_T;
-    static const std::vector<FusedEntry<T>> reg = [] {
-        std::vector<FusedEntry<T>> v;
-        constexpr int CH = TileC<T>::CH, CN = TileC<T>::CN;
-        using R32 = RadixList<4, 8>; using R64 = RadixList<8, 8>; using R128 = RadixList<16, 8>;
-        using R256 = RadixList<16, 16>; using R512 = RadixList<8, 8, 8>; using R1024 = RadixList<16, 8, 8>;
-        (void)CN;
-        if constexpr (sizeof(T) == 8) {
-            v.push_back(make_fused<T, R32, CN, 32, 0, R64, CH, 32, 0>());          // 2^11
-            v.push_back(make_fused<T, R64, CH, 32, 0, R64, CH, 32, 0>());          // 2^12
-            v.push_back(make_fused<T, R64, CH, 32, 0, R128, CH, 64, 0>());         // 2^13
-            v.push_back(make_fused<T, R128, CH, 64, 0, R128, CH, 64, 0>());        // 2^14
-            v.push_back(make_fused<T, R128, CH, 64, 0, R256, CH, 64, 0>());        // 2^15
-            v.push_back(make_fused<T, R256, CH, 64, 0, R256, CH, 64, 0>());        // 2^16
-            v.push_back(make_fused<T, R512, CH, 256, 3, R256, CH, 64, 0>());       // 2^17
-            v.push_back(make_fused<T, R512, CH, 256, 3, R512, CH, 256, 3>());      // 2^18
-            v.push_back(make_fused<T, R1024, CH, 512, 0, R512, CH, 256, 3>());     // 2^19
-            v.push_back(make_fused<T, RadixList<32, 32>, CN, 256, 0, RadixList<32, 32>, CN, 256, 0>());    // 2^20
-        } else {
-            v.push_back(make_fused<T, R64, CH, 32, 0, R128, CH, 64, 0>());         // 2^13
-            v.push_back(make_fused<T, R128, CH, 64, 0, R128, CH, 64, 0>());        // 2^14
-            v.push_back(make_fused<T, R128, CH, 64, 0, R256, CH, 128, 0>());       // 2^15
-            v.push_back(make_fused<T, R256, CH, 128, 0, R256, CH, 128, 0>());      // 2^16
-            v.push_back(make_fused<T, R512, CH, 256, 3, R256, CH, 128, 0>());      // 2^17
-            v.push_back(make_fused<T, R512, CH, 256, 3, R512, CH, 256, 3>());      // 2^18
-            v.push_back(make_fused<T, R1024, CH, 256, 0, R512, CH, 256, 3>());     // 2^19
-            v.push_back(make_fused<T, RadixList<32, 32>, CH, 256, 0, RadixList<32, 32>, CH, 256, 0>());    // 2^20
-        }
+    static const std::vector<PipeEntry<T>> reg = [] {
+        std::vector<PipeEntry<T>> v;
+        constexpr int CN = TileC<T>::CN, CH = TileC<T>::CH;
+        constexpr bool F64 = sizeof(T) == 8;
+        using R64 = RadixList<8, 8>; using R128 = RadixList<16, 8>; using R256 = RadixList<16, 16>; using R512 = RadixList<8, 8, 8>;
+        using R1024 = typename std::conditional<F64, RadixList<32, 32>, RadixList<16, 8, 8>>::type;
+        constexpr int NT256 = F64 ? 128 : 256, NT1024 = F64 ? 256 : 512;
+        // MINB: the register budget of the merged kernel is pinned to the occupancy its two passes have as separate kernels
+        // (left alone ptxas gives the loop 128 registers: 2 CTAs/SM instead of 3-4, measured 2.06 vs 1.39 ms on 4096 x 2^16 f32)
+        constexpr int M64 = F64 ? 8 : 10, M128 = F64 ? 4 : 6, M256 = F64 ? 4 : 4, M512 = 2, M1024 = 1;
+        v.push_back(make_pipe<T, R64, CN, 64, 0, R128, CN, 128, 0, M128>());         // 2^13 = {6,7}
+        v.push_back(make_pipe<T, R128, CN, 128, 0, R128, CN, 128, 0, M128>());       // 2^14
+        v.push_back(make_pipe<T, R128, CN, 128, 0, R256, CN, NT256, 0, M256>());     // 2^15 = {7,8}
+        v.push_back(make_pipe<T, R256, CN, NT256, 0, R256, CN, NT256, 0, M256>());   // 2^16
+        v.push_back(make_pipe<T, R512, CN, 256, 3, R256, CN, NT256, 0, M512>());     // 2^17 = {9,8}
+        v.push_back(make_pipe<T, R512, CN, 256, 3, R512, CN, 256, 3, M512>());       // 2^18
+        v.push_back(make_pipe<T, R1024, CN, NT1024, 0, R512, CN, 256, 3, M1024>());  // 2^19 = {10,9}
+        v.push_back(make_pipe<T, R1024, CN, NT1024, 0, R1024, CN, NT1024, 0, M1024>());  // 2^20
+        (void)M64; (void)CH;
         return v;
     }();
     return reg;

@@ -53,6 +53,14 @@ void add_strided_kernels<PHAST_T, PHAST_KIND>(std::vector<KernelEntry<PHAST_T>>&
     // id 62: the 1024-row tile at half width (64 KB f64 / 32 KB f32) for interleaved intermediates, register budget
     // pinned to 2 CTAs/SM (150 registers and 1 CTA/SM otherwise: 505 -> 713 us on the 2^26 middle pass)
     v.push_back(make_entry_v<T, KIND, CH, 256, 7, 2, 62, 16, 8, 8>());
+    // Asynchronous tile input (variant ids 3xx): the tile arrives by TMA (first pass: cp.async.bulk.tensor boxes of the
+    // planar arrays; last pass: cp.async.bulk copies of the contiguous rows of the interleaved workspace).  32-byte runs
+    // cost the LSU nothing this way, so a 1024-row tile can be 64 KB (CH columns) and three CTAs share an SM.
+    constexpr int MODE = KIND == KIND_COL ? MODE_TMA_IN : MODE_BULK_IN;
+    v.push_back(make_entry_async<T, KIND, CH, 32 * CH, MODE, 0, 3, 300, 32, 32>());      // 1024 rows, 64 KB tile
+    v.push_back(make_entry_async<T, KIND, CN, 32 * CN, MODE, 0, 1, 301, 32, 32>());      // 1024 rows, 128 KB tile
+    v.push_back(make_entry_async<T, KIND, CH, 32 * CH, MODE, 0, 3, 300, 16, 32>());      // 512 rows, 32 KB tile
+    v.push_back(make_entry_async<T, KIND, CN, 32 * CN, MODE, 0, 1, 301, 16, 32>());      // 512 rows, 64 KB tile
 }
 
 }  // namespace phast

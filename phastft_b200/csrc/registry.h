@@ -2,7 +2,7 @@
 //
 // The kernels are instantiated in several translation units so the library builds in parallel
 // (__graft_entry__.build()): reg_strided.cu (COL / TRANS passes, compiled once per precision and kind),
-// reg_row.cu (whole-transform-in-one-CTA kernels), reg_multi.cu (cluster and fused two-pass launches).
+// reg_row.cu (whole-transform-in-one-CTA kernels), reg_multi.cu (cluster and pipelined two-pass launches).
 // phastft_cuda.cu holds the planner, the launcher and the C ABI and only sees these descriptors.
 #pragma once
 #include <string>
@@ -15,6 +15,7 @@ namespace phast {
 template <typename T>
 struct KernelEntry {
     int kind, R, C, NT, first_radix, stages, variant;
+    int mode = 0;          // MODE_PLAIN, or MODE_TMA_IN / MODE_BULK_IN (asynchronous tile input)
     size_t smem;
     const void* fn;        // fft_pass_kernel<...>; NULL for the passes of a cluster launch (they only exist inside it)
     std::string radices;
@@ -30,9 +31,10 @@ struct ClusterEntry {
     size_t smem;
 };
 
-// Both passes of a 2-pass plan of a lone L2-resident transform in one launch with a grid barrier (fft_fused2_kernel).
+// Both passes of a 2-pass plan in one persistent launch, intermediates in an L2-resident ring (fft_pipe2_kernel).
+// Matched to a plan by the descriptors of its two pass kernels.
 template <typename T>
-struct FusedEntry {
+struct PipeEntry {
     int R1, C1, NT1, R2, C2, NT2;
     std::string rad1, rad2;
     const void* fn;
@@ -66,13 +68,30 @@ KernelEntry<T> make_entry_v() {
     if (ID) e.radices += ",v" + std::to_string(ID);
     return e;
 }
+// pass kernels with an asynchronous tile input (cp.async.bulk.tensor / cp.async.bulk + mbarrier)
+template <typename T, int KIND, int C, int NT, int MODE, int VARIANT, int MINB, int ID, int... Rs>
+KernelEntry<T> make_entry_async() {
+    using RL = RadixList<Rs...>;
+    using PK = PassKernel<T, RL, C, NT, KIND, MODE, VARIANT>;
+    static_assert(NT % 32 == 0, "whole warps");
+    static_assert(KIND != KIND_COL || NT % C == 0, "a COL thread keeps its column");
+    static_assert(PK::SMEM_BYTES <= 227 * 1024, "tile exceeds the 227 KB shared memory of an sm_100 CTA");
+    KernelEntry<T> e;
+    e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.variant = ID; e.mode = MODE;
+    e.smem = PK::SMEM_BYTES;
+    e.fn = reinterpret_cast<const void*>(&fft_pass_async_kernel<T, RL, C, NT, KIND, MODE, VARIANT, MINB>);
+    e.radices = radix_string<RL>() + (MODE == MODE_TMA_IN ? ",tma" : ",bulk");
+    if (ID) e.radices += ",v" + std::to_string(ID);
+    return e;
+}
+
 template <typename T, int KIND, int C, int NT, int... Rs>
 KernelEntry<T> make_entry() { return make_entry_v<T, KIND, C, NT, 0, 0, 0, Rs...>(); }
 
 // defined in the reg_*.cu translation units
 template <typename T> void add_row_kernels(std::vector<KernelEntry<T>>& v);
 template <typename T, int KIND> void add_strided_kernels(std::vector<KernelEntry<T>>& v);
-template <typename T> const std::vector<FusedEntry<T>>& fused_registry();
+template <typename T> const std::vector<PipeEntry<T>>& pipe_registry();
 template <typename T> const std::vector<ClusterEntry<T>>& cluster_registry();
 
 }  // namespace phast

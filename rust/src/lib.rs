@@ -117,6 +117,76 @@ pub fn fft_32_dit(reals: &mut [f32], imags: &mut [f32], direction: Direction) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Additive: batches and device-resident data.  The reference has no batch API -- a batch is a caller loop sharing one
+// planner (examples/benchmark.rs:24-36); on a GPU the loop is one call, and the data can stay in device memory.
+// ------------------------------------------------------------------------------------------------
+
+macro_rules! impl_batch {
+    ($batch:ident, $sharded:ident, $device:ident, $t:ty, $planner:ident, $ffi_sharded:ident, $ffi_dev:ident) => {
+        /// `batch` transforms of `planner.num_points()` points, transform `b` at `[b * batch_stride ..][.. n]` of the planar
+        /// host slices, in place; equivalent to calling the `_with_planner` function on every transform.  Host memory is
+        /// streamed through a three-slot H2D / FFT / D2H pipeline (page-lock it with [`host_register`] for full PCIe speed).
+        pub fn $batch(reals: &mut [$t], imags: &mut [$t], direction: Direction, planner: &$planner, batch: usize, batch_stride: usize) {
+            $sharded(reals, imags, direction, &[planner], batch, batch_stride);
+        }
+        /// The same batch sharded over several devices from one process: transforms `[g*batch/G, (g+1)*batch/G)` run on
+        /// `planners[g]` (one planner per device).  No data-path collective.
+        pub fn $sharded(reals: &mut [$t], imags: &mut [$t], direction: Direction, planners: &[&$planner], batch: usize, batch_stride: usize) {
+            assert!(!planners.is_empty(), "at least one planner");
+            let n = planners[0].num_points();
+            assert_eq!(reals.len(), imags.len(), "reals.len() == imags.len()");
+            assert!(batch_stride >= n && (batch == 0 || reals.len() >= (batch - 1) * batch_stride + n), "slices shorter than batch * batch_stride");
+            let raw: Vec<*mut _> = planners.iter().map(|p| p.raw).collect();
+            check(unsafe { ffi::$ffi_sharded(raw.as_ptr(), raw.len() as i32, reals.as_mut_ptr(), imags.as_mut_ptr(), batch, batch_stride, direction as i32) });
+        }
+        /// Device-resident planar data: stream-ordered on `stream` (a `cudaStream_t`, null = the default stream), no
+        /// allocation, no host synchronisation.
+        ///
+        /// # Safety
+        /// `d_reals` / `d_imags` must be device pointers valid for `(batch - 1) * batch_stride + n` elements on the
+        /// planner's device, and must not be used by other work on other streams until this call's work has completed.
+        pub unsafe fn $device(d_reals: *mut $t, d_imags: *mut $t, direction: Direction, planner: &$planner, batch: usize, batch_stride: usize,
+                              stream: *mut std::os::raw::c_void) {
+            check(ffi::$ffi_dev(planner.raw, d_reals, d_imags, direction as i32, batch, batch_stride, stream));
+        }
+    };
+}
+impl_batch!(fft_64_dit_batch, fft_64_dit_batch_sharded, fft_64_dit_device, f64, PlannerDit64, phastft_fft_dit_f64_batch_sharded_host, phastft_fft_dit_f64_dev);
+impl_batch!(fft_32_dit_batch, fft_32_dit_batch_sharded, fft_32_dit_device, f32, PlannerDit32, phastft_fft_dit_f32_batch_sharded_host, phastft_fft_dit_f32_dev);
+
+/// Number of CUDA devices the library sees (0 without a driver; every transform then panics with the NO_DEVICE message).
+pub fn device_count() -> usize {
+    let mut n: std::os::raw::c_int = 0;
+    unsafe { ffi::phastft_device_count(&mut n) };
+    n.max(0) as usize
+}
+
+/// Device-resident real transforms (`r2c.rs:535`, `:740` on device pointers).
+///
+/// # Safety
+/// Device pointers on the planner's device: `d_input` N reals, `d_out_*` N/2 + 1 each.
+pub unsafe fn r2c_fft_f64_device(d_input: *const f64, d_out_re: *mut f64, d_out_im: *mut f64, planner: &PlannerR2c64, stream: *mut std::os::raw::c_void) {
+    check(ffi::phastft_r2c_f64_dev(planner.raw, d_input, d_out_re, d_out_im, stream));
+}
+/// # Safety
+/// As [`r2c_fft_f64_device`]; `d_scratch_*` are N/2 each or both null (the plan's own scratch is then used).
+pub unsafe fn c2r_fft_f64_device(d_in_re: *const f64, d_in_im: *const f64, d_output: *mut f64, planner: &PlannerR2c64,
+                                 d_scratch_re: *mut f64, d_scratch_im: *mut f64, stream: *mut std::os::raw::c_void) {
+    check(ffi::phastft_c2r_f64_dev(planner.raw, d_in_re, d_in_im, d_output, d_scratch_re, d_scratch_im, stream));
+}
+/// # Safety
+/// As [`r2c_fft_f64_device`].
+pub unsafe fn r2c_fft_f32_device(d_input: *const f32, d_out_re: *mut f32, d_out_im: *mut f32, planner: &PlannerR2c32, stream: *mut std::os::raw::c_void) {
+    check(ffi::phastft_r2c_f32_dev(planner.raw, d_input, d_out_re, d_out_im, stream));
+}
+/// # Safety
+/// As [`c2r_fft_f64_device`].
+pub unsafe fn c2r_fft_f32_device(d_in_re: *const f32, d_in_im: *const f32, d_output: *mut f32, planner: &PlannerR2c32,
+                                 d_scratch_re: *mut f32, d_scratch_im: *mut f32, stream: *mut std::os::raw::c_void) {
+    check(ffi::phastft_c2r_f32_dev(planner.raw, d_in_re, d_in_im, d_output, d_scratch_re, d_scratch_im, stream));
+}
+
+// ------------------------------------------------------------------------------------------------
 // r2c / c2r  (algorithms/r2c.rs:521-895)
 // ------------------------------------------------------------------------------------------------
 
@@ -130,8 +200,11 @@ pub fn r2c_fft_f64_with_planner(input_re: &[f64], output_re: &mut [f64], output_
 
 /// `r2c.rs:521`
 pub fn r2c_fft_f64(input_re: &[f64], output_re: &mut [f64], output_im: &mut [f64]) {
-    let planner = PlannerR2c64::new(input_re.len());
-    r2c_fft_f64_with_planner(input_re, output_re, output_im, &planner);
+    // a planner per call, as in the reference; the library keeps the latest one for the next same-size call
+    check(unsafe {
+        ffi::phastft_r2c_f64_oneshot(input_re.as_ptr(), input_re.len(), output_re.as_mut_ptr(), output_re.len(),
+                                     output_im.as_mut_ptr(), output_im.len(), device())
+    });
 }
 
 /// `r2c.rs:607`
@@ -144,8 +217,10 @@ pub fn r2c_fft_f32_with_planner(input_re: &[f32], output_re: &mut [f32], output_
 
 /// `r2c.rs:598`
 pub fn r2c_fft_f32(input_re: &[f32], output_re: &mut [f32], output_im: &mut [f32]) {
-    let planner = PlannerR2c32::new(input_re.len());
-    r2c_fft_f32_with_planner(input_re, output_re, output_im, &planner);
+    check(unsafe {
+        ffi::phastft_r2c_f32_oneshot(input_re.as_ptr(), input_re.len(), output_re.as_mut_ptr(), output_re.len(),
+                                     output_im.as_mut_ptr(), output_im.len(), device())
+    });
 }
 
 /// `r2c.rs:740` -- caller scratch is length-checked like the reference; the work happens in device memory.
@@ -168,8 +243,9 @@ pub fn c2r_fft_f64_with_planner(input_re: &[f64], input_im: &[f64], output: &mut
 
 /// `r2c.rs:695`
 pub fn c2r_fft_f64(input_re: &[f64], input_im: &[f64], output: &mut [f64]) {
-    let planner = PlannerR2c64::new(output.len());
-    c2r_fft_f64_with_planner(input_re, input_im, output, &planner);
+    check(unsafe {
+        ffi::phastft_c2r_f64_oneshot(input_re.as_ptr(), input_re.len(), input_im.as_ptr(), input_im.len(), output.as_mut_ptr(), output.len(), device())
+    });
 }
 
 /// `r2c.rs:835`
@@ -192,8 +268,9 @@ pub fn c2r_fft_f32_with_planner(input_re: &[f32], input_im: &[f32], output: &mut
 
 /// `r2c.rs:804`
 pub fn c2r_fft_f32(input_re: &[f32], input_im: &[f32], output: &mut [f32]) {
-    let planner = PlannerR2c32::new(output.len());
-    c2r_fft_f32_with_planner(input_re, input_im, output, &planner);
+    check(unsafe {
+        ffi::phastft_c2r_f32_oneshot(input_re.as_ptr(), input_re.len(), input_im.as_ptr(), input_im.len(), output.as_mut_ptr(), output.len(), device())
+    });
 }
 
 // ------------------------------------------------------------------------------------------------

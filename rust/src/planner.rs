@@ -11,7 +11,9 @@ pub enum Direction {
     Reverse = -1,
 }
 
-/// `planner.rs:25-32` (accepted and ignored, as in the reference: `planner.rs:65`)
+/// `planner.rs:25-32`.  The reference accepts the mode and ignores it (`planner.rs:65`); here `Tune` is real: the
+/// planner builds a handful of pass decompositions / tile widths around the heuristic one, times them on the device
+/// and keeps the fastest.
 #[derive(Copy, Clone, Debug, Default)]
 pub enum PlannerMode {
     #[default]
@@ -20,7 +22,7 @@ pub enum PlannerMode {
 }
 
 macro_rules! impl_planner_dit {
-    ($name:ident, $raw:ty, $create:ident, $destroy:ident) => {
+    ($name:ident, $raw:ty, $create:ident, $destroy:ident, $size:ident, $describe:ident, $reserve:ident) => {
         pub struct $name {
             pub(crate) raw: *mut $raw,
         }
@@ -37,6 +39,20 @@ macro_rules! impl_planner_dit {
                 check(unsafe { ffi::$create(num_points, device(), mode as i32, &mut raw) });
                 Self { raw }
             }
+            /// Number of points the planner was built for.
+            pub fn num_points(&self) -> usize {
+                unsafe { ffi::$size(self.raw) }
+            }
+            /// Additive: the pass decomposition and kernels the planner chose, e.g.
+            /// `"n=2^20 f64: COL R=1024(32x32) C=8 NT=256 | TRANS R=1024(32x32) C=8 NT=256"`.
+            pub fn describe(&self) -> String {
+                unsafe { std::ffi::CStr::from_ptr(ffi::$describe(self.raw)) }.to_string_lossy().into_owned()
+            }
+            /// Additive: size the device workspace for calls of up to `batch` transforms now (otherwise the first larger
+            /// batched call grows it, synchronising the device).
+            pub fn reserve(&self, batch: usize) {
+                check(unsafe { ffi::$reserve(self.raw, batch) });
+            }
         }
         impl Drop for $name {
             fn drop(&mut self) {
@@ -45,8 +61,10 @@ macro_rules! impl_planner_dit {
         }
     };
 }
-impl_planner_dit!(PlannerDit64, ffi::phastft_plan_dit_f64, phastft_plan_dit_f64_create, phastft_plan_dit_f64_destroy);
-impl_planner_dit!(PlannerDit32, ffi::phastft_plan_dit_f32, phastft_plan_dit_f32_create, phastft_plan_dit_f32_destroy);
+impl_planner_dit!(PlannerDit64, ffi::phastft_plan_dit_f64, phastft_plan_dit_f64_create, phastft_plan_dit_f64_destroy,
+                  phastft_plan_dit_f64_size, phastft_plan_dit_f64_describe, phastft_plan_dit_f64_reserve);
+impl_planner_dit!(PlannerDit32, ffi::phastft_plan_dit_f32, phastft_plan_dit_f32_create, phastft_plan_dit_f32_destroy,
+                  phastft_plan_dit_f32_size, phastft_plan_dit_f32_describe, phastft_plan_dit_f32_reserve);
 
 macro_rules! impl_planner_r2c {
     ($name:ident, $raw:ty, $create:ident, $destroy:ident) => {

@@ -115,3 +115,21 @@ def test_planner_factorization_host_logic(pf):
     assert _lib.plan_factorization(1 << 16, 32) == [8, 8]
     with pytest.raises(pf.PhastFTPanic):
         _lib.plan_factorization(12, 64)
+
+
+def test_rust_ffi_is_generated_from_the_header():
+    """rust/src/ffi.rs binds every PHASTFT_API declaration: it is the output of tools/gen_rust_ffi.py on the current header."""
+    import importlib.util
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", root / "tools" / "gen_rust_ffi.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert (root / "rust" / "src" / "ffi.rs").read_text() == mod.render()
+    names = {n for n, _, _ in mod.declarations()}
+    assert len(names) >= 60 and "phastft_fft_dit_f32_batch_sharded_host" in names and "phastft_plan_dit_f64_reserve" in names
+    # the safe layer reaches the measured path: batch, device pointers, describe
+    lib_rs = (root / "rust" / "src" / "lib.rs").read_text() + (root / "rust" / "src" / "planner.rs").read_text()
+    for item in ("fn fft_64_dit_batch", "fn fft_32_dit_batch", "fn fft_32_dit_batch_sharded", "fn fft_64_dit_device", "fn describe", "fn reserve",
+                 "phastft_r2c_f64_oneshot", "phastft_c2r_f32_oneshot"):
+        assert item in lib_rs or item.replace("fn ", "") in lib_rs, item

@@ -291,27 +291,35 @@ def test_config_2pow26_f64_properties_and_oracle():
 
 
 def test_config_batch_f32_2pow16_linearity_and_oracle():
+    """BASELINE.json configs[3] at FULL size: 4096 x 2^16 f32 in one batched call (2 GiB per array pair).  Size-independent
+    property on the whole batch: linearity FFT(a + b) = FFT(a) + FFT(b); oracle parity for 16 members spread over the batch
+    (incl. both ends); every member's DC bin against the sum of its input (cheap, all 4096)."""
     import torch
     pf, O = _pf(), _O()
-    n, batch = 1 << 16, 256                        # a slice of the 4096-transform config (same kernels, same plan)
+    n, batch = 1 << 16, 4096
     planner = pf.PlannerDit32(n)
-    rng = np.random.default_rng(1234)
-    a = rng.uniform(-1, 1, (2, batch * n)).astype(np.float32)
-    b = rng.uniform(-1, 1, (2, batch * n)).astype(np.float32)
-
-    def run(re, im):
-        d_re = torch.from_numpy(re.copy()).cuda(); d_im = torch.from_numpy(im.copy()).cuda()
-        pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, planner, batch)
-        return d_re.cpu().numpy(), d_im.cpu().numpy()
-
-    A = run(a[0], a[1]); B = run(b[0], b[1]); S = run(a[0] + b[0], a[1] + b[1])
-    lin = max(np.max(np.abs(S[0] - (A[0] + B[0]))), np.max(np.abs(S[1] - (A[1] + B[1]))))
-    assert lin / np.max(np.abs(S[0])) < 64 * np.finfo(np.float32).eps
-    for t in (0, 17, batch - 1):
-        s = slice(t * n, (t + 1) * n)
-        o_re, o_im = a[0][s].copy(), a[1][s].copy()
+    planner.reserve(batch)
+    g = torch.Generator(device="cuda"); g.manual_seed(1234)
+    a_re = torch.rand(batch * n, device="cuda", generator=g) * 2 - 1; a_im = torch.rand(batch * n, device="cuda", generator=g) * 2 - 1
+    members = sorted({0, 1, 255, 256, 1023, 1024, 2047, 2048, 2049, 3000, 3071, 3072, 4000, 4094, 4095, 17})
+    keep = {t: (a_re[t * n:(t + 1) * n].cpu().numpy().copy(), a_im[t * n:(t + 1) * n].cpu().numpy().copy()) for t in members}
+    dc_re = a_re.view(batch, n).double().sum(dim=1); dc_im = a_im.view(batch, n).double().sum(dim=1)
+    b_re = torch.rand(batch * n, device="cuda", generator=g) * 2 - 1; b_im = torch.rand(batch * n, device="cuda", generator=g) * 2 - 1
+    s_re = a_re + b_re; s_im = a_im + b_im
+    for re, im in ((a_re, a_im), (b_re, b_im), (s_re, s_im)):
+        pf.fft_dit_batch(re, im, pf.Direction.Forward, planner, batch)
+    lin = max(float((s_re - (a_re + b_re)).abs().max()), float((s_im - (a_im + b_im)).abs().max()))
+    assert lin / float(s_re.abs().max()) < 64 * np.finfo(np.float32).eps
+    # DC bin of every member = sum of its inputs
+    got_dc_re = a_re.view(batch, n)[:, 0].double(); got_dc_im = a_im.view(batch, n)[:, 0].double()
+    scale = float(a_re.abs().max())
+    assert float((got_dc_re - dc_re).abs().max()) / scale < 16 * np.finfo(np.float32).eps * np.log2(n)
+    assert float((got_dc_im - dc_im).abs().max()) / scale < 16 * np.finfo(np.float32).eps * np.log2(n)
+    for t in members:
+        o_re, o_im = keep[t][0].copy(), keep[t][1].copy()
         O.fft_dit(o_re, o_im, O.FORWARD)
-        assert rel_linf(A[0][s], A[1][s], o_re, o_im) <= tol(np.float32, n)
+        s = slice(t * n, (t + 1) * n)
+        assert rel_linf(a_re[s].cpu().numpy(), a_im[s].cpu().numpy(), o_re, o_im) <= tol(np.float32, n), t
 
 
 # --- PlannerMode::Tune is real here: it must stay correct and never be slower than the heuristic plan ----

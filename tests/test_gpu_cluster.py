@@ -47,11 +47,13 @@ SIZES = [(np.float64, 13), (np.float64, 14), (np.float64, 15), (np.float64, 16),
 
 @pytest.mark.parametrize("dt,log_n", SIZES)
 @pytest.mark.parametrize("direction", ["Forward", "Reverse"])
-def test_batched_single_pass_vs_oracle(dt, log_n, direction):
+def test_batched_single_pass_vs_oracle(dt, log_n, direction, monkeypatch):
     """A batch large enough to take the cluster / one-CTA path: every 7th member against the oracle, all members against
     the lone-transform path (another radix split, so tolerance not bit equality), padding between members untouched."""
     import torch
     pf, O = _pf(), _O()
+    monkeypatch.setenv("PHASTFT_CLUSTER", "1")          # both mechanisms are opt-in (measured slower than two launches)
+    monkeypatch.setenv("PHASTFT_ONE_CTA_MAX", "14")
     n, batch = 1 << log_n, 41
     stride = n + 24
     rng = np.random.default_rng(100 * log_n + batch)
@@ -141,6 +143,7 @@ def test_cluster_variants_agree(dt, log_n, variant, monkeypatch):
     import torch
     pf, O = _pf(), _O()
     monkeypatch.setenv("PHASTFT_CLUSTER_VARIANT", str(variant))
+    monkeypatch.setenv("PHASTFT_ONE_CTA_MAX", "12")
     n, batch = 1 << log_n, 19
     planner = planner_cls(dt)(n, 0)
     assert f",v{variant}" in planner.describe(), planner.describe()
@@ -154,3 +157,52 @@ def test_cluster_variants_agree(dt, log_n, variant, monkeypatch):
         o_re, o_im = re_h[s].copy(), im_h[s].copy()
         O.fft_dit(o_re, o_im, O.FORWARD)
         assert rel_linf(g_re[s], g_im[s], o_re, o_im) <= tol(dt, n)
+
+
+# ---- asynchronous (TMA) tile input for the two passes of a lone 2^18..2^20-point transform -------------------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("log_n", [18, 19, 20])
+@pytest.mark.parametrize("variant", [300, 301])
+def test_tma_tile_input_vs_oracle(dt, log_n, variant, monkeypatch):
+    """cp.async.bulk.tensor boxes of the planar input (first pass) and cp.async.bulk rows of the interleaved workspace (last
+    pass) feed the same stages as the plain loads: oracle parity forward and reverse, and agreement with the plain kernels."""
+    pf, O = _pf(), _O()
+    n = 1 << log_n
+    monkeypatch.setenv("PHASTFT_TMA_VARIANT", str(variant))
+    planner = planner_cls(dt)(n, 0)
+    assert ",tma" in planner.describe() and ",bulk" in planner.describe(), planner.describe()
+    monkeypatch.setenv("PHASTFT_TMA", "0")
+    plain = planner_cls(dt)(n, 0)
+    assert ",tma" not in plain.describe()
+    fft = pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
+    rng = np.random.default_rng(variant + log_n)
+    re0 = rng.uniform(-1, 1, n).astype(dt); im0 = rng.uniform(-1, 1, n).astype(dt)
+    for direction, od in ((pf.Direction.Forward, O.FORWARD), (pf.Direction.Reverse, O.REVERSE)):
+        a, b = re0.copy(), im0.copy()
+        fft(a, b, direction, planner)
+        c, d = re0.copy(), im0.copy()
+        fft(c, d, direction, plain)
+        o_re, o_im = re0.copy(), im0.copy()
+        O.fft_dit(o_re, o_im, od)
+        assert rel_linf(a, b, o_re, o_im) <= tol(dt, n)
+        assert rel_linf(a, b, c, d) <= tol(dt, n)
+
+
+def test_tma_path_in_a_stream_of_calls():
+    """Back-to-back calls on one stream (programmatic dependent launch lets the next grid start early): every result must
+    still be the transform of its own input, in place, including when consecutive calls reuse the same buffers."""
+    import torch
+    pf = _pf()
+    n = 1 << 20
+    planner = pf.PlannerDit64(n, 0)
+    rng = np.random.default_rng(5)
+    sigs = [(rng.uniform(-1, 1, n), rng.uniform(-1, 1, n)) for _ in range(3)]
+    dev = [(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in sigs]
+    for rep in range(2):                         # forward then reverse on the same buffers, all calls queued without a sync
+        for a, b in dev:
+            pf.fft_64_dit_with_planner(a, b, pf.Direction.Forward, planner)
+        for a, b in dev:
+            pf.fft_64_dit_with_planner(a, b, pf.Direction.Reverse, planner)
+    torch.cuda.synchronize()
+    for (a, b), (ha, hb) in zip(dev, sigs):
+        assert np.max(np.abs(a.cpu().numpy() - ha)) < 1e-10 and np.max(np.abs(b.cpu().numpy() - hb)) < 1e-10

@@ -4,11 +4,13 @@ import numpy as np
 import pytest
 
 
-@pytest.mark.multigpu
+@pytest.mark.gpu
 def test_batch_sharded_matches_single_device():
+    """Runs with however many devices the box has (the driver's `-m gpu` box has one: the sharded entry point then degenerates
+    to one shard, which still exercises the partition and the host pipeline; with 2-8 devices it is the cross-device check)."""
     import torch
     import phastft_b200 as pf
-    G = min(torch.cuda.device_count(), 4)
+    G = max(1, min(torch.cuda.device_count(), 8))
     n, batch = 1 << 16, 64
     rng = np.random.default_rng(1234)
     re = rng.uniform(-1, 1, batch * n).astype(np.float32)

@@ -10,6 +10,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <string>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -281,6 +283,109 @@ __global__ void __launch_bounds__(NT) k_l2_exchange(int iters, double2* scratch,
     if (sink) sink[(long long)blockIdx.x * NT + threadIdx.x] = acc;
 }
 
+
+// 5. L2 bandwidth: grid-stride copy / read of a buffer that fits the 126 MB L2, repeated (first repetition warms L2)
+__global__ void __launch_bounds__(512) k_l2_copy(const double2* __restrict__ in, double2* __restrict__ out, long long n2, int reps) {
+    for (int r = 0; r < reps; ++r)
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) out[i] = __ldcg(in + i);
+}
+__global__ void __launch_bounds__(512) k_l2_read(const double2* __restrict__ in, double* sink, long long n2, int reps) {
+    double acc = 0;
+    for (int r = 0; r < reps; ++r) {
+        long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        for (; i + 3LL * gridDim.x * blockDim.x < n2; i += 4LL * gridDim.x * blockDim.x) {
+            double2 a = __ldcg(in + i), b = __ldcg(in + i + (long long)gridDim.x * blockDim.x), c = __ldcg(in + i + 2LL * gridDim.x * blockDim.x),
+                    d = __ldcg(in + i + 3LL * gridDim.x * blockDim.x);
+            acc += a.x + b.y + c.x + d.y;
+        }
+    }
+    if (acc == 1.2345) sink[0] = acc;
+}
+void bench_l2(size_t mib) {
+    const long long n2 = (long long)(mib << 20) / 16;
+    double2 *a, *b; double* sink;
+    CK(cudaMalloc(&a, n2 * 16)); CK(cudaMalloc(&b, n2 * 16)); CK(cudaMalloc(&sink, 8));
+    CK(cudaMemset(a, 0, n2 * 16));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 20;
+    for (int mode = 0; mode < 2; ++mode) {
+        for (int w = 0; w < 2; ++w) { if (mode) k_l2_read<<<148 * 4, 512>>>(a, sink, n2, 2); else k_l2_copy<<<148 * 4, 512>>>(a, b, n2, 2); }
+        cudaEventRecord(e0);
+        if (mode) k_l2_read<<<148 * 4, 512>>>(a, sink, n2, reps); else k_l2_copy<<<148 * 4, 512>>>(a, b, n2, reps);
+        cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = (double)reps * n2 * 16 * (mode ? 1 : 2);
+        printf("L2 %s of %4zu MiB %s: %7.2f TB/s\n", mode ? "read" : "copy", mib, mode ? "            " : "(read+write)", bytes / (ms * 1e-3) / 1e12);
+    }
+    CK(cudaFree(a)); CK(cudaFree(b)); CK(cudaFree(sink));
+}
+
+
+// 6. Does an L2-sized ring of intermediates save the HBM round trip?  Persistent CTAs; work item i: copy tile i of `in` into
+// ring slot (i % ring_tiles) of `ws`, and copy the tile written `delay` items ago from the ring to `out`.  With ring = the whole
+// array this is two full HBM copies (what a two-launch plan moves); with an L2-sized ring the middle write+read should stay in L2.
+// hint: 0 plain ld/st, 1 streaming (.cs) for in/out and .cg for the ring
+__global__ void __launch_bounds__(256) k_ring(const double2* __restrict__ in, double2* __restrict__ out, double2* ws, long long tiles, int tile_elems,
+                                              long long ring_tiles, int delay, int hint, unsigned long long* ticket) {
+    __shared__ long long s_item;
+    for (;;) {
+        if (threadIdx.x == 0) s_item = (long long)atomicAdd(ticket, 1ULL);
+        __syncthreads();
+        const long long item = s_item;
+        __syncthreads();
+        if (item >= tiles + delay) break;
+        if (item < tiles) {
+            const double2* src = in + item * tile_elems;
+            double2* dst = ws + (item % ring_tiles) * tile_elems;
+            for (int e = threadIdx.x; e < tile_elems; e += 4 * blockDim.x) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = hint ? __ldcs(src + e + u * blockDim.x) : src[e + u * blockDim.x];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { if (hint) __stcg(dst + e + u * blockDim.x, v[u]); else dst[e + u * blockDim.x] = v[u]; }
+            }
+        }
+        if (item >= delay) {
+            const long long j = item - delay;
+            const double2* src = ws + (j % ring_tiles) * tile_elems;
+            double2* dst = out + j * tile_elems;
+            for (int e = threadIdx.x; e < tile_elems; e += 4 * blockDim.x) {
+                double2 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = hint ? __ldcg(src + e + u * blockDim.x) : src[e + u * blockDim.x];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { if (hint) __stcs(dst + e + u * blockDim.x, v[u]); else dst[e + u * blockDim.x] = v[u]; }
+            }
+        }
+    }
+}
+void bench_ring() {
+    const long long total = 2048LL << 20;                 // 2 GiB in, 2 GiB out
+    const int tile_bytes = 32 * 1024, tile_elems = tile_bytes / 16;
+    const long long tiles = total / tile_bytes;
+    double2 *in, *out, *ws; unsigned long long* ticket;
+    CK(cudaMalloc(&in, total)); CK(cudaMalloc(&out, total)); CK(cudaMalloc(&ws, total)); CK(cudaMalloc(&ticket, 8));
+    CK(cudaMemset(in, 0, total));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int hint = 0; hint < 2; ++hint)
+        for (long long ring_mb : {2048LL, 96LL, 64LL, 48LL, 32LL, 16LL}) {
+            const long long ring_tiles = (ring_mb << 20) / tile_bytes;
+            const int delay = (int)std::min<long long>(ring_tiles / 2, tiles / 2);     // read back half a ring later
+            float best = 1e9f;
+            for (int rep = 0; rep < 3; ++rep) {
+                CK(cudaMemset(ticket, 0, 8));
+                cudaEventRecord(e0);
+                k_ring<<<148 * 4, 256>>>(in, out, ws, tiles, tile_elems, ring_tiles, delay, hint, ticket);
+                cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                best = std::min(best, ms);
+            }
+            printf("ring pipeline hint=%d ring=%5lld MiB delay=%6d tiles: %8.1f us -> %5.2f TB/s of compulsory traffic (2 GiB in + 2 GiB out)\n", hint, ring_mb, delay,
+                   best * 1e3, 2.0 * total / (best * 1e-3) / 1e12);
+        }
+    CK(cudaFree(in)); CK(cudaFree(out)); CK(cudaFree(ws)); CK(cudaFree(ticket));
+}
+
 template <typename F>
 void launch_cluster(F kernel, int grid, int nt, size_t smem, int K, void** args) {
     if (smem > 227 * 1024) { printf("  (skipped: %zu bytes of shared memory)\n", smem); return; }
@@ -426,6 +531,8 @@ int main(int argc, char** argv) {
     CK(cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0));
     printf("SMs %d, clock %d kHz\n", sms, clk);
 
+    if (argc > 1 && std::string(argv[1]) == "ring") { bench_ring(); return 0; }
+    if (argc > 1 && std::string(argv[1]) == "l2") { for (size_t m : {8, 16, 32, 48, 64, 256, 1024}) bench_l2(m); return 0; }
     // ---- 3. cluster.sync ----
     bench_csync<2>(64); bench_csync<4>(32); bench_csync<8>(16); bench_csync<16>(8);
 
