@@ -206,3 +206,36 @@ def test_tma_path_in_a_stream_of_calls():
     torch.cuda.synchronize()
     for (a, b), (ha, hb) in zip(dev, sigs):
         assert np.max(np.abs(a.cpu().numpy() - ha)) < 1e-10 and np.max(np.abs(b.cpu().numpy() - hb)) < 1e-10
+
+
+# ---- pipelined two-pass launch: one grid runs both passes, intermediates in an L2-resident ring of workspace slots ----
+@pytest.mark.parametrize("dt,log_n,batch", [(np.float32, 16, 300), (np.float64, 16, 70), (np.float64, 14, 1100), (np.float32, 14, 700),
+                                            (np.float64, 18, 20), (np.float32, 20, 9)])
+@pytest.mark.parametrize("ring_mb", [1, 32])
+def test_pipelined_launch_is_bit_identical_to_two_launches(dt, log_n, batch, ring_mb, monkeypatch):
+    """fft_pipe2_kernel runs the same two pass bodies as the two-launch plan (same kernels, same tables), so the results must be
+    bit-identical; a 1 MiB ring forces many wrap-arounds of the workspace slots (the pass-1 tiles then really wait for pass 2 to
+    drain their slot, and pass 2 discards its input lines from L2), 32 MiB is the default."""
+    import torch
+    pf = _pf()
+    n = 1 << log_n
+    rng = np.random.default_rng(log_n * 1000 + batch)
+    re_h = rng.uniform(-1, 1, batch * n).astype(dt); im_h = rng.uniform(-1, 1, batch * n).astype(dt)
+    monkeypatch.setenv("PHASTFT_PIPE", "0")
+    plain = planner_cls(dt)(n, 0)
+    assert "pipelined" not in plain.describe()
+    a_re = torch.from_numpy(re_h).cuda(); a_im = torch.from_numpy(im_h).cuda()
+    pf.fft_dit_batch(a_re, a_im, pf.Direction.Forward, plain, batch)
+    monkeypatch.setenv("PHASTFT_PIPE", "1")
+    monkeypatch.setenv("PHASTFT_PIPE_RING_MB", str(ring_mb))
+    piped = planner_cls(dt)(n, 0)
+    assert "one pipelined launch" in piped.describe(), piped.describe()
+    b_re = torch.from_numpy(re_h).cuda(); b_im = torch.from_numpy(im_h).cuda()
+    before = pf.launch_count()
+    pf.fft_dit_batch(b_re, b_im, pf.Direction.Forward, piped, batch)
+    assert pf.launch_count() - before == 1
+    assert torch.equal(a_re, b_re) and torch.equal(a_im, b_im)
+    # and the inverse brings the input back
+    pf.fft_dit_batch(b_re, b_im, pf.Direction.Reverse, piped, batch)
+    err = max(float((b_re.cpu() - torch.from_numpy(re_h)).abs().max()), float((b_im.cpu() - torch.from_numpy(im_h)).abs().max()))
+    assert err <= (1e-10 if dt == np.float64 else 3e-6)
