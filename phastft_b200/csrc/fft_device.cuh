@@ -187,6 +187,147 @@ template <typename T> struct Dft<T, 32> {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Complex-array interface of the DFTs: DftC<T, RAD>::run(x[RAD]) and ctwid(a, w) = a * w.
+//
+// double: unpacks into the split re/im arrays above (same operations, same order).
+// float:  Blackwell's packed single-precision arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 on 64-bit register pairs,
+//         __fadd2_rn / __fmul2_rn / __ffma2_rn).  A complex value is one register pair, so a complex add is ONE instruction,
+//         a twiddled butterfly three (lo + w*hi as two chained FFMA2 -- the half-swap and the sign pattern of (-hi.y, hi.x)
+//         fold into the instruction's operand modifiers -- then 2*lo - out0 as one), a multiplication by -j none at all
+//         (operand modifiers of the consuming add).  Every component sees the same operations in the same order as the
+//         scalar forms above (the reference's fma(2, lo, -out0) butterfly, kernels/dit.rs:181-183), in half the issue slots:
+//         the f32 passes are issue-bound once their HBM traffic is out of the way (profiles/r02_tuning.md).
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ cx<T> ctwid(const cx<T>& a, const cx<T>& w) { return cmul<T>(a, w); }
+template <typename T> __device__ __forceinline__ cx<T> cscale(const cx<T>& a, T s) { return make_cx<T>(a.x * s, a.y * s); }
+
+template <typename T, int RAD> struct DftC {
+    static __device__ __forceinline__ void run(cx<T> (&x)[RAD]) {
+        T r[RAD], i[RAD];
+#pragma unroll
+        for (int k = 0; k < RAD; ++k) { r[k] = x[k].x; i[k] = x[k].y; }
+        Dft<T, RAD>::run(r, i);
+#pragma unroll
+        for (int k = 0; k < RAD; ++k) x[k] = make_cx<T>(r[k], i[k]);
+    }
+};
+
+namespace pk {   // packed float2 helpers
+__device__ __forceinline__ float2 add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 mj(float2 a) { return make_float2(a.y, -a.x); }    // a * (-j)
+__device__ __forceinline__ float2 pj(float2 a) { return make_float2(-a.y, a.x); }    // a * (+j)
+// lo + w * h
+__device__ __forceinline__ float2 cfma(float2 lo, float2 h, float2 w) { return fma(pj(h), bc(w.y), fma(h, bc(w.x), lo)); }
+// (lo, hi) -> (lo + w*hi, lo - w*hi), generic twiddle: 3 packed instructions
+__device__ __forceinline__ void bf_w(float2& lo, float2& hi, float wr, float wi) {
+    const float2 o0 = cfma(lo, hi, make_float2(wr, wi));
+    hi = fma(lo, bc(2.0f), make_float2(-o0.x, -o0.y));
+    lo = o0;
+}
+__device__ __forceinline__ void bf_1(float2& lo, float2& hi) { const float2 a = add(lo, hi); hi = sub(lo, hi); lo = a; }
+__device__ __forceinline__ void bf_mj(float2& lo, float2& hi) { const float2 t = mj(hi); const float2 a = add(lo, t); hi = sub(lo, t); lo = a; }
+// w = (1 - j)/sqrt2 : w*hi = s * (hi + (-j) hi)
+__device__ __forceinline__ void bf_w8_1(float2& lo, float2& hi) {
+    const float s = 0.70710678118654752440084436210484903928f;
+    const float2 o0 = fma(add(hi, mj(hi)), bc(s), lo);
+    hi = fma(lo, bc(2.0f), make_float2(-o0.x, -o0.y));
+    lo = o0;
+}
+// w = (-1 - j)/sqrt2 : w*hi = s * ((-j) hi - hi)
+__device__ __forceinline__ void bf_w8_3(float2& lo, float2& hi) {
+    const float s = 0.70710678118654752440084436210484903928f;
+    const float2 o0 = fma(sub(mj(hi), hi), bc(s), lo);
+    hi = fma(lo, bc(2.0f), make_float2(-o0.x, -o0.y));
+    lo = o0;
+}
+}  // namespace pk
+
+template <> __device__ __forceinline__ float2 cscale<float>(const float2& a, float s) { return pk::mul(a, pk::bc(s)); }
+template <> __device__ __forceinline__ float2 ctwid<float>(const float2& a, const float2& w) {
+    return pk::fma(pk::pj(a), pk::bc(w.y), pk::mul(a, pk::bc(w.x)));
+}
+
+template <> struct DftC<float, 1> { static __device__ __forceinline__ void run(float2 (&)[1]) {} };
+template <> struct DftC<float, 2> { static __device__ __forceinline__ void run(float2 (&x)[2]) { pk::bf_1(x[0], x[1]); } };
+template <> struct DftC<float, 4> {
+    static __device__ __forceinline__ void run(float2 (&x)[4]) {
+        pk::bf_1(x[0], x[2]);
+        pk::bf_1(x[1], x[3]);
+        pk::bf_1(x[0], x[1]);     // x0 = X0, x1 = X2
+        pk::bf_mj(x[2], x[3]);    // x2 = X1, x3 = X3
+        const float2 t = x[1]; x[1] = x[2]; x[2] = t;
+    }
+};
+template <> struct DftC<float, 8> {
+    static __device__ __forceinline__ void run(float2 (&x)[8]) {
+        float2 e[4] = {x[0], x[2], x[4], x[6]}, o[4] = {x[1], x[3], x[5], x[7]};
+        DftC<float, 4>::run(e);
+        DftC<float, 4>::run(o);
+        pk::bf_1(e[0], o[0]);
+        pk::bf_w8_1(e[1], o[1]);
+        pk::bf_mj(e[2], o[2]);
+        pk::bf_w8_3(e[3], o[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { x[k] = e[k]; x[k + 4] = o[k]; }
+    }
+};
+template <> struct DftC<float, 16> {
+    static __device__ __forceinline__ void run(float2 (&x)[16]) {
+        float2 e[8], o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
+        DftC<float, 8>::run(e);
+        DftC<float, 8>::run(o);
+        const float c1 = 0.92387953251128675612818318939678828682f;  // cos(pi/8)
+        const float s1 = 0.38268343236508977172845998403039886676f;  // sin(pi/8)
+        pk::bf_1(e[0], o[0]);
+        pk::bf_w(e[1], o[1], c1, -s1);
+        pk::bf_w8_1(e[2], o[2]);
+        pk::bf_w(e[3], o[3], s1, -c1);
+        pk::bf_mj(e[4], o[4]);
+        pk::bf_w(e[5], o[5], -s1, -c1);
+        pk::bf_w8_3(e[6], o[6]);
+        pk::bf_w(e[7], o[7], -c1, -s1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { x[k] = e[k]; x[k + 8] = o[k]; }
+    }
+};
+template <> struct DftC<float, 32> {
+    static __device__ __forceinline__ void run(float2 (&x)[32]) {
+        float2 e[16], o[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { e[k] = x[2 * k]; o[k] = x[2 * k + 1]; }
+        DftC<float, 16>::run(e);
+        DftC<float, 16>::run(o);
+        const float c1 = 0.980785280403230449126182236134239036973934f, s1 = 0.195090322016128267848284868477022240927692f;
+        const float c2 = 0.923879532511286756128183189396788286822417f, s2 = 0.382683432365089771728459984030398866761345f;
+        const float c3 = 0.831469612302545237078788377617905756738561f, s3 = 0.555570233019602224742830813948532874374937f;
+        pk::bf_1(e[0], o[0]);
+        pk::bf_w(e[1], o[1], c1, -s1);
+        pk::bf_w(e[2], o[2], c2, -s2);
+        pk::bf_w(e[3], o[3], c3, -s3);
+        pk::bf_w8_1(e[4], o[4]);
+        pk::bf_w(e[5], o[5], s3, -c3);
+        pk::bf_w(e[6], o[6], s2, -c2);
+        pk::bf_w(e[7], o[7], s1, -c1);
+        pk::bf_mj(e[8], o[8]);
+        pk::bf_w(e[9], o[9], -s1, -c1);
+        pk::bf_w(e[10], o[10], -s2, -c2);
+        pk::bf_w(e[11], o[11], -s3, -c3);
+        pk::bf_w8_3(e[12], o[12]);
+        pk::bf_w(e[13], o[13], -c3, -s3);
+        pk::bf_w(e[14], o[14], -c2, -s2);
+        pk::bf_w(e[15], o[15], -c1, -s1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { x[k] = e[k]; x[k + 16] = o[k]; }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Compile-time radix lists.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr int ilog2_c(int v) { return v <= 1 ? 0 : 1 + ilog2_c(v >> 1); }

@@ -216,45 +216,45 @@ struct PassKernel {
     // selects, and the selects of the interleaved path split its loads into two dependent batches).
     // Layout class: 0 planar, 1 interleaved (re, im), 2 interleaved swapped (im, re), -1 = test at run time.
     template <int N, int IL = -1>
-    static __device__ __forceinline__ void gload_n(const PassParams<T>& p, long long a0, long long step, T (&re)[N], T (&im)[N]) {
+    static __device__ __forceinline__ void gload_n(const PassParams<T>& p, long long a0, long long step, cx<T> (&x)[N]) {
         if constexpr (IL < 0) {
-            if (p.in_interleaved == 0) gload_n<N, 0>(p, a0, step, re, im);
-            else if (p.in_interleaved == 1) gload_n<N, 1>(p, a0, step, re, im);
-            else gload_n<N, 2>(p, a0, step, re, im);
+            if (p.in_interleaved == 0) gload_n<N, 0>(p, a0, step, x);
+            else if (p.in_interleaved == 1) gload_n<N, 1>(p, a0, step, x);
+            else gload_n<N, 2>(p, a0, step, x);
         } else if constexpr (IL == 0) {
             const T* pr = p.in_re + a0;
             const T* pi = p.in_im + a0;
 #pragma unroll
-            for (int i = 0; i < N; ++i) { re[i] = pr[(long long)i * step]; im[i] = pi[(long long)i * step]; }
+            for (int i = 0; i < N; ++i) x[i] = make_cx<T>(pr[(long long)i * step], pi[(long long)i * step]);
         } else {
             const cx<T>* pc = reinterpret_cast<const cx<T>*>(p.in_re) + a0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 const cx<T> v = pc[(long long)i * step];
-                if constexpr (IL == 1) { re[i] = v.x; im[i] = v.y; } else { re[i] = v.y; im[i] = v.x; }
+                x[i] = (IL == 1) ? v : make_cx<T>(v.y, v.x);
             }
         }
     }
     template <int N, int OL = -1>
-    static __device__ __forceinline__ void gstore_n(const PassParams<T>& p, long long a0, long long step, T (&re)[N], T (&im)[N]) {
+    static __device__ __forceinline__ void gstore_n(const PassParams<T>& p, long long a0, long long step, cx<T> (&x)[N]) {
         if constexpr (OL < 0) {
-            if (p.out_interleaved == 0) gstore_n<N, 0>(p, a0, step, re, im);
-            else if (p.out_interleaved == 1) gstore_n<N, 1>(p, a0, step, re, im);
-            else gstore_n<N, 2>(p, a0, step, re, im);
+            if (p.out_interleaved == 0) gstore_n<N, 0>(p, a0, step, x);
+            else if (p.out_interleaved == 1) gstore_n<N, 1>(p, a0, step, x);
+            else gstore_n<N, 2>(p, a0, step, x);
         } else {
             if (p.scale != T(1)) {
 #pragma unroll
-                for (int i = 0; i < N; ++i) { re[i] *= p.scale; im[i] *= p.scale; }
+                for (int i = 0; i < N; ++i) x[i] = cscale<T>(x[i], p.scale);
             }
             if constexpr (OL == 0) {
                 T* pr = p.out_re + a0;
                 T* pi = p.out_im + a0;
 #pragma unroll
-                for (int i = 0; i < N; ++i) { pr[(long long)i * step] = re[i]; pi[(long long)i * step] = im[i]; }
+                for (int i = 0; i < N; ++i) { pr[(long long)i * step] = x[i].x; pi[(long long)i * step] = x[i].y; }
             } else {
                 cx<T>* pc = reinterpret_cast<cx<T>*>(p.out_re) + a0;
 #pragma unroll
-                for (int i = 0; i < N; ++i) pc[(long long)i * step] = (OL == 1) ? make_cx<T>(re[i], im[i]) : make_cx<T>(im[i], re[i]);
+                for (int i = 0; i < N; ++i) pc[(long long)i * step] = (OL == 1) ? x[i] : make_cx<T>(x[i].y, x[i].x);
             }
         }
     }
@@ -278,39 +278,27 @@ struct PassKernel {
             const int m = j & (NS - 1);
             const int g = j / NS;
             const int base = g * NS * RAD + m;
-            T xr[RAD], xi[RAD];
+            cx<T> x[RAD];
 #pragma unroll
-            for (int i = 0; i < RAD; ++i) {
-                cx<T> v = tile[Addr::at(base + i * NS, c)];
-                xr[i] = v.x; xi[i] = v.y;
-            }
+            for (int i = 0; i < RAD; ++i) x[i] = tile[Addr::at(base + i * NS, c)];
             if constexpr ((VARIANT & 2) && RAD == 8) {
                 // 3 table loads (W^m, W^2m, W^4m), the other four twiddles by complex products
                 cx<T> w1 = __ldg(p.tw_stage + ((m * 1) << TW_SHIFT));
                 cx<T> w2 = __ldg(p.tw_stage + ((m * 2) << TW_SHIFT));
                 cx<T> w4 = __ldg(p.tw_stage + ((m * 4) << TW_SHIFT));
-                cx<T> w3 = cmul<T>(w1, w2), w5 = cmul<T>(w1, w4), w6 = cmul<T>(w2, w4);
-                cx<T> w7 = cmul<T>(w3, w4);
+                cx<T> w3 = ctwid<T>(w1, w2), w5 = ctwid<T>(w1, w4), w6 = ctwid<T>(w2, w4);
+                cx<T> w7 = ctwid<T>(w3, w4);
                 const cx<T> ws[8] = {w1, w1, w2, w3, w4, w5, w6, w7};
 #pragma unroll
-                for (int i = 1; i < RAD; ++i) {
-                    T a = xr[i], b = xi[i];
-                    xr[i] = fma_t(-b, ws[i].y, a * ws[i].x);
-                    xi[i] = fma_t(b, ws[i].x, a * ws[i].y);
-                }
+                for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], ws[i]);
             } else {
 #pragma unroll
-                for (int i = 1; i < RAD; ++i) {
-                    cx<T> w = __ldg(p.tw_stage + ((m * i) << TW_SHIFT));
-                    T a = xr[i], b = xi[i];
-                    xr[i] = fma_t(-b, w.y, a * w.x);
-                    xi[i] = fma_t(b, w.x, a * w.y);
-                }
+                for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], __ldg(p.tw_stage + ((m * i) << TW_SHIFT)));
             }
-            Dft<T, RAD>::run(xr, xi);
+            DftC<T, RAD>::run(x);
             if constexpr (!LAST) {
 #pragma unroll
-                for (int k = 0; k < RAD; ++k) tile[Addr::at(base + k * NS, c)] = make_cx<T>(xr[k], xi[k]);
+                for (int k = 0; k < RAD; ++k) tile[Addr::at(base + k * NS, c)] = x[k];
             } else if constexpr (XCH == 1) {
                 // last stage of the producing pass of a cluster exchange.  Output row h = m + k*NS of this CTA's column
                 // tcol belongs, in the next pass, to CTA h / CB of the cluster, which wants it at [h % CB][tcol] of its tile
@@ -326,13 +314,13 @@ struct PassKernel {
                 for (int k = 0; k < RAD; ++k) {
                     const unsigned h = (unsigned)(m + k * NS);
                     const unsigned off = ((h & cb_mask) << p.xch_log2P2) + tcol;
-                    st_cluster(map_to_rank(tile_s + off * (unsigned)sizeof(cx<T>), h >> p.xch_log2CB), make_cx<T>(xr[k], xi[k]));
+                    st_cluster(map_to_rank(tile_s + off * (unsigned)sizeof(cx<T>), h >> p.xch_log2CB), x[k]);
                 }
             } else {
                 // last stage: g == 0, natural-order outputs kr = m + k*NS
                 if (KIND == KIND_ROW && c >= tile_rows_valid) continue;
-                if constexpr (KIND == KIND_ROW) gstore_n<RAD, OL>(p, out_base + (long long)c * p.out_bstride + m, (long long)NS, xr, xi);
-                else gstore_n<RAD, OL>(p, out_base + (long long)m * out_kstride + c, (long long)NS * out_kstride, xr, xi);
+                if constexpr (KIND == KIND_ROW) gstore_n<RAD, OL>(p, out_base + (long long)c * p.out_bstride + m, (long long)NS, x);
+                else gstore_n<RAD, OL>(p, out_base + (long long)m * out_kstride + c, (long long)NS * out_kstride, x);
             }
         }
     }
@@ -458,7 +446,7 @@ struct PassKernel {
         // dependent L2 round trips that would otherwise sit in front of the first data load).
         constexpr bool PRELOAD = (M * C <= NT);
         static_assert((XCH != 2 && !ASYNC_IN) || PRELOAD, "a pass that reads its input out of its own tile must do stage 1 in a single trip (every thread holds its task's inputs across the barrier)");
-        T pre_r[PRELOAD ? R1 : 1], pre_i[PRELOAD ? R1 : 1];
+        cx<T> pre[PRELOAD ? R1 : 1];
         if constexpr (PRELOAD) {
             const int t = tid;
             if (t < M * C) {
@@ -470,13 +458,13 @@ struct PassKernel {
                     // the previous pass's CTAs left this tile as [c][t], t = mp + i*M (what the global loads would have read)
                     const cx<T>* src = tile + c * R + mp;
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) { const cx<T> v = src[i * M]; pre_r[i] = v.x; pre_i[i] = v.y; }
+                    for (int i = 0; i < R1; ++i) pre[i] = src[i * M];
                 } else if ((KIND != KIND_ROW) || (c < rows_valid)) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
-                    gload_n<R1>(p, a0, (long long)M * in_rstride, pre_r, pre_i);
+                    gload_n<R1>(p, a0, (long long)M * in_rstride, pre);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) { pre_r[i] = T(0); pre_i[i] = T(0); }
+                    for (int i = 0; i < R1; ++i) pre[i] = make_cx<T>(T(0), T(0));
                 }
             }
         }
@@ -519,11 +507,11 @@ struct PassKernel {
                     const T* re_pl = reinterpret_cast<const T*>(tile) + mp * C + c;
                     const T* im_pl = re_pl + R * C;
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) { pre_r[i] = re_pl[i * M * C]; pre_i[i] = im_pl[i * M * C]; }
+                    for (int i = 0; i < R1; ++i) pre[i] = make_cx<T>(re_pl[i * M * C], im_pl[i * M * C]);
                 } else {
                     const cx<T>* src = tile + c * R + mp;
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) { const cx<T> v = src[i * M]; pre_r[i] = v.x; pre_i[i] = v.y; }
+                    for (int i = 0; i < R1; ++i) pre[i] = src[i * M];
                 }
             }
             __syncthreads();     // the landing zone is free: stage 1 may overwrite it
@@ -539,48 +527,39 @@ struct PassKernel {
             for (int t = tid; t < NTASK; t += NT) {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
-                T xr[R1], xi[R1];
+                cx<T> x[R1];
                 [[maybe_unused]] const bool valid = (KIND != KIND_ROW) || (c < rows_valid);
                 if constexpr (PRELOAD) {
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) { xr[i] = pre_r[i]; xi[i] = pre_i[i]; }
+                    for (int i = 0; i < R1; ++i) x[i] = pre[i];
                 } else if (valid) {
                     const long long a0 = in_base + (long long)c * in_cstride + (long long)mp * in_rstride;
-                    gload_n<R1, IL>(p, a0, (long long)M * in_rstride, xr, xi);
+                    gload_n<R1, IL>(p, a0, (long long)M * in_rstride, x);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) { xr[i] = T(0); xi[i] = T(0); }
+                    for (int i = 0; i < R1; ++i) x[i] = make_cx<T>(T(0), T(0));
                 }
                 if (has_tw) {
                     cx<T> pt = s_um[mp];
                     if constexpr (KIND == KIND_COL) {
-                        pt = cmul<T>(pt, vreg);
+                        pt = ctwid<T>(pt, vreg);
                     } else {
-                        if (kp_cstep) pt = cmul<T>(pt, __ldg(p.tw_wc + c * M + mp));
+                        if (kp_cstep) pt = ctwid<T>(pt, __ldg(p.tw_wc + c * M + mp));
                     }
                     const cx<T>* g = (KIND == KIND_TRANS) ? (s_g + c * R1) : s_g;
-                    {
-                        T a = xr[0], b = xi[0];
-                        xr[0] = fma_t(-b, pt.y, a * pt.x);
-                        xi[0] = fma_t(b, pt.x, a * pt.y);
-                    }
+                    x[0] = ctwid<T>(x[0], pt);
 #pragma unroll
-                    for (int i = 1; i < R1; ++i) {
-                        cx<T> w = cmul<T>(pt, g[i]);
-                        T a = xr[i], b = xi[i];
-                        xr[i] = fma_t(-b, w.y, a * w.x);
-                        xi[i] = fma_t(b, w.x, a * w.y);
-                    }
+                    for (int i = 1; i < R1; ++i) x[i] = ctwid<T>(x[i], ctwid<T>(pt, g[i]));
                 }
-                Dft<T, R1>::run(xr, xi);
+                DftC<T, R1>::run(x);
                 if constexpr (S >= 2) {
                     const int j = rev_tail<RL>(mp);
 #pragma unroll
-                    for (int k = 0; k < R1; ++k) tile[Addr::at(j * R1 + k, c)] = make_cx<T>(xr[k], xi[k]);
+                    for (int k = 0; k < R1; ++k) tile[Addr::at(j * R1 + k, c)] = x[k];
                 } else {
                     if (valid) {
-                        if constexpr (KIND == KIND_ROW) gstore_n<R1>(p, out_base + (long long)c * p.out_bstride, 1LL, xr, xi);
-                        else gstore_n<R1>(p, out_base + c, out_kstride, xr, xi);
+                        if constexpr (KIND == KIND_ROW) gstore_n<R1>(p, out_base + (long long)c * p.out_bstride, 1LL, x);
+                        else gstore_n<R1>(p, out_base + c, out_kstride, x);
                     }
                 }
             }

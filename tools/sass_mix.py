@@ -32,7 +32,7 @@ for line in out.splitlines():
         n += 1
 print("static instructions:", n)
 cls = collections.Counter()
-FP = {"DFMA", "DADD", "DMUL", "FFMA", "FADD", "FMUL", "HFMA2"}
+FP = {"DFMA", "DADD", "DMUL", "FFMA", "FADD", "FMUL", "HFMA2", "FFMA2", "FADD2", "FMUL2"}
 MEM = lambda o: o.split(".")[0] in ("LDS", "STS", "LDG", "STG", "LD", "ST", "LDL", "STL")
 for op, c in ops.items():
     cls["fp" if op in FP else "mem" if MEM(op) else "other"] += c
