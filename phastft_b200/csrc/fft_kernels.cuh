@@ -422,15 +422,22 @@ struct PassKernel {
                 mbar_expect_tx(mbar, (unsigned)(TILE_ELEMS * sizeof(cx<T>)));
                 const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
                 if constexpr (XCH == MODE_TMA_IN) {
-                    // landing zone: re plane [R][C] then im plane [R][C]; boxes of at most 256 rows
+                    // boxes of at most 256 rows.  Planar input: re plane [R][C] then im plane [R][C].  Interleaved input (the
+                    // workspace of a 3-pass plan): one map over the pairs, the landing zone is the tile itself, [R][C] complex.
                     constexpr int BOX_ROWS = R < 256 ? R : 256;
                     const int blkq = (int)(tile_index + (unsigned)p.blk_offset);
                     const int col0 = (blkq & ((1 << (p.log2B - LOG2C)) - 1)) << LOG2C;
-                    const int bz = blkq >> (p.log2B - LOG2C);          // first pass: log2A == 0, the rest is the batch index
+                    const int bz = blkq >> (p.log2B - LOG2C);          // = a + A * batch: the map's third dimension
+                    if (p.in_interleaved) {
 #pragma unroll
-                    for (int r0 = 0; r0 < R; r0 += BOX_ROWS) {
-                        tma_load_3d(tile_s + (unsigned)(r0 * C * sizeof(T)), &p.tmap_re, col0, r0, bz, mbar);
-                        tma_load_3d(tile_s + (unsigned)((R + r0) * C * sizeof(T)), &p.tmap_im, col0, r0, bz, mbar);
+                        for (int r0 = 0; r0 < R; r0 += BOX_ROWS)
+                            tma_load_3d(tile_s + (unsigned)(r0 * C * sizeof(cx<T>)), &p.tmap_re, 2 * col0, r0, bz, mbar);
+                    } else {
+#pragma unroll
+                        for (int r0 = 0; r0 < R; r0 += BOX_ROWS) {
+                            tma_load_3d(tile_s + (unsigned)(r0 * C * sizeof(T)), &p.tmap_re, col0, r0, bz, mbar);
+                            tma_load_3d(tile_s + (unsigned)((R + r0) * C * sizeof(T)), &p.tmap_im, col0, r0, bz, mbar);
+                        }
                     }
                 } else {
                     const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in_re) + in_base;
@@ -504,10 +511,16 @@ struct PassKernel {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
                 if constexpr (XCH == MODE_TMA_IN) {
-                    const T* re_pl = reinterpret_cast<const T*>(tile) + mp * C + c;
-                    const T* im_pl = re_pl + R * C;
+                    if (p.in_interleaved) {
+                        const cx<T>* src = tile + mp * C + c;
 #pragma unroll
-                    for (int i = 0; i < R1; ++i) pre[i] = make_cx<T>(re_pl[i * M * C], im_pl[i * M * C]);
+                        for (int i = 0; i < R1; ++i) pre[i] = src[i * M * C];
+                    } else {
+                        const T* re_pl = reinterpret_cast<const T*>(tile) + mp * C + c;
+                        const T* im_pl = re_pl + R * C;
+#pragma unroll
+                        for (int i = 0; i < R1; ++i) pre[i] = make_cx<T>(re_pl[i * M * C], im_pl[i * M * C]);
+                    }
                 } else {
                     const cx<T>* src = tile + c * R + mp;
 #pragma unroll

@@ -503,6 +503,15 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             off = (off + 255) & ~size_t(255);
         }
     }
+    // 3-pass plans with interleaved intermediates: the 1024-row middle pass with its tile arriving by TMA (64 KB landing zone =
+    // the tile, no register-staged loads: three CTAs per SM each with its whole tile in flight).  PHASTFT_TMA_MID=0|1.
+    if (pl->num_passes == 3 && il3) {
+        int enabled = 1;
+        if (const char* env = getenv("PHASTFT_TMA_MID")) enabled = atoi(env);
+        if (enabled && tensor_map_encoder())
+            for (const auto& e : registry<T>())
+                if (e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.variant == 300 && e.R == (1 << f[1]) && e.C <= (1 << pl->pass[1].log2B)) pl->pass[1].kt = &e;
+    }
     // Batches of transforms that one CTA can hold (128 KB tile: 2^13 f64, 2^14 f32) use a one-CTA kernel: one launch,
     // one HBM round trip.  PHASTFT_ONE_CTA_MAX (log2) lowers the limit for re-tuning.
     // 2^13 f64 / 2^14 f32 in one CTA (128 KB tile, one CTA per SM) measured slower than two passes of small tiles
@@ -681,6 +690,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                      " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
             }
         }
+        if (pl->num_passes == 3 && pl->pass[1].kt) {
+            const auto* k = pl->pass[1].kt;
+            s += " [middle pass by TMA: COL R=" + std::to_string(k->R) + "(" + k->radices + ") C=" + std::to_string(k->C) + " NT=" + std::to_string(k->NT) + "]";
+        }
         if (pl->l2_group) s += " | L2-blocked tail: " + std::to_string(pl->l2_group) + " k1/group";
         bool differs = false;
         for (int p = 0; p < pl->num_passes; ++p) differs |= pl->pass[p].kb && pl->pass[p].kb != pl->pass[p].k;
@@ -745,11 +758,19 @@ int32_t launch_pass(const Plan<T>& pl, int p, const PassParams<T>& base, size_t 
     int32_t st = prepare_pass(pl, p, base, batch, k1_lo, k1_cnt, prm, k, blocks, use_kt);
     if (st) return st;
     if (k->mode == MODE_TMA_IN) {
-        const size_t B = size_t(1) << prm.log2B;
+        const size_t B = size_t(1) << prm.log2B, A = size_t(1) << prm.log2A;
         const unsigned box_rows = (unsigned)std::min(k->R, 256);
-        if (!encode_tile_map<T>(&prm.tmap_re, prm.in_re, B, (size_t)k->R, B, batch, (size_t)prm.in_bstride, (unsigned)k->C, box_rows) ||
-            !encode_tile_map<T>(&prm.tmap_im, prm.in_im, B, (size_t)k->R, B, batch, (size_t)prm.in_bstride, (unsigned)k->C, box_rows))
-            return fail(PHASTFT_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        bool ok;
+        if (prm.in_interleaved) {
+            // the interleaved workspace as an array of T: rows of 2B values, A * batch blocks of R rows (batch stride = A * R * B pairs)
+            if (batch > 1 && (size_t)prm.in_bstride != A * (size_t)k->R * B) return fail(PHASTFT_ERR_INVALID_ARG, "TMA middle pass: the workspace must be dense");
+            ok = encode_tile_map<T>(&prm.tmap_re, prm.in_re, 2 * B, (size_t)k->R, 2 * B, A * batch, (size_t)k->R * 2 * B, 2u * (unsigned)k->C, box_rows);
+        } else {
+            if (A != 1) return fail(PHASTFT_ERR_INVALID_ARG, "TMA planar input: first pass only");
+            ok = encode_tile_map<T>(&prm.tmap_re, prm.in_re, B, (size_t)k->R, B, batch, (size_t)prm.in_bstride, (unsigned)k->C, box_rows) &&
+                 encode_tile_map<T>(&prm.tmap_im, prm.in_im, B, (size_t)k->R, B, batch, (size_t)prm.in_bstride, (unsigned)k->C, box_rows);
+        }
+        if (!ok) return fail(PHASTFT_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     }
     void* args[] = {&prm};
     // Programmatic dependent launch: measured no gain with 128 KB tiles (the next grid cannot become resident early), -10%
@@ -1120,7 +1141,8 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
                 prm.out_interleaved = il;
             }
             if (pass_events && done == 0 && p == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
-            int32_t st = launch_pass(pl, p, prm, nb, stream, 0, -1, tma);
+            const bool tma_mid = P == 3 && p == 1 && pl.pass[1].kt != nullptr && il == 1 && nb == 1;
+            int32_t st = launch_pass(pl, p, prm, nb, stream, 0, -1, tma || tma_mid);
             if (st) return st;
             if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[p + 1], stream));
         }

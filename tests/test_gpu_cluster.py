@@ -239,3 +239,35 @@ def test_pipelined_launch_is_bit_identical_to_two_launches(dt, log_n, batch, rin
     pf.fft_dit_batch(b_re, b_im, pf.Direction.Reverse, piped, batch)
     err = max(float((b_re.cpu() - torch.from_numpy(re_h)).abs().max()), float((b_im.cpu() - torch.from_numpy(im_h)).abs().max()))
     assert err <= (1e-10 if dt == np.float64 else 3e-6)
+
+
+@pytest.mark.parametrize("dt,log_n", [(np.float64, 25), (np.float32, 25), (np.float64, 26)])
+def test_tma_middle_pass_of_three_pass_plans(dt, log_n, monkeypatch):
+    """2^25 / 2^26: the middle pass gets its tile by TMA from the interleaved workspace.  Same transform as with the plain middle
+    pass (another radix split: tolerance), DC bin and Parseval as size-independent checks, forward -> reverse round trip."""
+    import torch
+    pf = _pf()
+    n = 1 << log_n
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    g = torch.Generator(device="cuda"); g.manual_seed(log_n)
+    re0 = torch.rand(n, dtype=tdt, device="cuda", generator=g) * 2 - 1; im0 = torch.rand(n, dtype=tdt, device="cuda", generator=g) * 2 - 1
+    fft = pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
+    monkeypatch.setenv("PHASTFT_TMA_MID", "0")
+    plain = planner_cls(dt)(n, 0)
+    assert "middle pass by TMA" not in plain.describe()
+    a_re, a_im = re0.clone(), im0.clone()
+    fft(a_re, a_im, pf.Direction.Forward, plain)
+    monkeypatch.setenv("PHASTFT_TMA_MID", "1")
+    tma = planner_cls(dt)(n, 0)
+    assert "middle pass by TMA" in tma.describe(), tma.describe()
+    b_re, b_im = re0.clone(), im0.clone()
+    fft(b_re, b_im, pf.Direction.Forward, tma)
+    scale = float(torch.maximum(a_re.abs().max(), a_im.abs().max()))
+    err = max(float((a_re - b_re).abs().max()), float((a_im - b_im).abs().max())) / scale
+    assert err <= tol(dt, n), err
+    eps = np.finfo(dt).eps
+    assert abs(float(b_re[0]) - float(re0.double().sum())) <= 64 * eps * np.sqrt(n) * np.log2(n)
+    e_in = float((re0.double() ** 2 + im0.double() ** 2).sum()); e_out = float((b_re.double() ** 2 + b_im.double() ** 2).sum()) / n
+    assert abs(e_out - e_in) / e_in <= 64 * eps * np.log2(n)
+    fft(b_re, b_im, pf.Direction.Reverse, tma)
+    assert max(float((b_re - re0).abs().max()), float((b_im - im0).abs().max())) <= (1e-10 if dt == np.float64 else 3e-5)
