@@ -506,11 +506,17 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
     // 3-pass plans with interleaved intermediates: the 1024-row middle pass with its tile arriving by TMA (64 KB landing zone =
     // the tile, no register-staged loads: three CTAs per SM each with its whole tile in flight).  PHASTFT_TMA_MID=0|1.
     if (pl->num_passes == 3 && il3) {
-        int enabled = 1;
+        int enabled = 1, ends = 0;
         if (const char* env = getenv("PHASTFT_TMA_MID")) enabled = atoi(env);
-        if (enabled && tensor_map_encoder())
-            for (const auto& e : registry<T>())
-                if (e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.variant == 300 && e.R == (1 << f[1]) && e.C <= (1 << pl->pass[1].log2B)) pl->pass[1].kt = &e;
+        if (const char* env = getenv("PHASTFT_TMA_ENDS")) ends = atoi(env);
+        if (tensor_map_encoder())
+            for (const auto& e : registry<T>()) {
+                if (e.variant != 300) continue;
+                if (enabled && e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.R == (1 << f[1]) && e.C == TileC<T>::CH) pl->pass[1].kt = &e;
+                // the 128-byte-run end passes: planar boxes in (first pass), contiguous rows of the workspace in (last pass)
+                if (ends && e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.R == (1 << f[0]) && e.C == TileC<T>::CW) pl->pass[0].kt = &e;
+                if (ends && e.mode == MODE_BULK_IN && e.kind == KIND_TRANS && e.R == (1 << f[2]) && e.C == TileC<T>::CW) pl->pass[2].kt = &e;
+            }
     }
     // Batches of transforms that one CTA can hold (128 KB tile: 2^13 f64, 2^14 f32) use a one-CTA kernel: one launch,
     // one HBM round trip.  PHASTFT_ONE_CTA_MAX (log2) lowers the limit for re-tuning.
@@ -650,12 +656,18 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         int enabled = 0, lone = 0;        // opt-in until it beats two launches (profiles/r02_exp_pipe_kernel_v*.txt)
         if (const char* e = getenv("PHASTFT_PIPE")) enabled = atoi(e);
         if (const char* e = getenv("PHASTFT_PIPE_LONE")) lone = atoi(e);
+        int want_mode = 0;                 // PHASTFT_PIPE_TMA=1: the pair with asynchronous tile input, where one exists
+        if (const char* e = getenv("PHASTFT_PIPE_TMA")) want_mode = atoi(e) != 0;
         auto find = [&](const KernelEntry<T>* a, const KernelEntry<T>* b) -> const PipeEntry<T>* {
             if (!a || !b) return nullptr;
+            const PipeEntry<T>* plain = nullptr;
             for (const auto& pe : pipe_registry<T>())
                 if (pe.R1 == a->R && pe.C1 == a->C && pe.NT1 == a->NT && pe.rad1 == a->radices && pe.R2 == b->R && pe.C2 == b->C &&
-                    pe.NT2 == b->NT && pe.rad2 == b->radices) return &pe;
-            return nullptr;
+                    pe.NT2 == b->NT && pe.rad2 == b->radices) {
+                    if (pe.mode == want_mode && tensor_map_encoder()) return &pe;
+                    if (pe.mode == 0) plain = &pe;
+                }
+            return plain;
         };
         auto resident = [&](const PipeEntry<T>* pe) -> int {
             int occ = 0, sms = 0;
@@ -694,6 +706,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             const auto* k = pl->pass[1].kt;
             s += " [middle pass by TMA: COL R=" + std::to_string(k->R) + "(" + k->radices + ") C=" + std::to_string(k->C) + " NT=" + std::to_string(k->NT) + "]";
         }
+        if (pl->num_passes == 3 && pl->pass[0].kt && pl->pass[2].kt) s += " [end passes by TMA / bulk copies, C=" + std::to_string(pl->pass[0].kt->C) + "]";
         if (pl->l2_group) s += " | L2-blocked tail: " + std::to_string(pl->l2_group) + " k1/group";
         bool differs = false;
         for (int p = 0; p < pl->num_passes; ++p) differs |= pl->pass[p].kb && pl->pass[p].kb != pl->pass[p].k;
@@ -706,7 +719,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             }
         }
         if (pl->num_passes >= 2) s += pl->ws_il == 1 ? " [interleaved intermediates]" : pl->ws_il == 0 ? " [planar intermediates]" : "";
-        if (pl->pipe_b) s += " [batches: one pipelined launch, " + std::to_string(pl->pipe_grid_b) + " resident CTAs, L2 ring]";
+        if (pl->pipe_b) s += std::string(" [batches: one pipelined launch, ") + (pl->pipe_b->mode ? "TMA / bulk tile input, " : "") + std::to_string(pl->pipe_grid_b) + " resident CTAs, L2 ring]";
         if (pl->pipe_1) s += " [lone: one pipelined launch, " + std::to_string(pl->pipe_grid_1) + " resident CTAs]";
         if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
         if (pl->cl)
@@ -1043,6 +1056,16 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
         if (st) return st;
         if (k1->R != pipe->R1 || k1->C != pipe->C1 || k2->R != pipe->R2 || k2->C != pipe->C2)
             return fail(PHASTFT_ERR_INVALID_ARG, "pipelined launch: kernel pair does not match the plan");
+        if (pipe->mode == 1) {
+            const size_t B = size_t(1) << p1.log2B;
+            const bool ok_align = io.in_il == 0 && il_p == 1 && ((reinterpret_cast<uintptr_t>(io.in_re) | reinterpret_cast<uintptr_t>(io.in_im)) & 15) == 0 &&
+                                  ((size_t)io.in_bstride * sizeof(T)) % 16 == 0;
+            if (!ok_align) return fail(PHASTFT_ERR_INVALID_ARG, "pipelined launch with TMA input needs planar 16-byte-aligned input (unset PHASTFT_PIPE_TMA)");
+            const unsigned box_rows = (unsigned)std::min(k1->R, 256);
+            if (!encode_tile_map<T>(&p1.tmap_re, p1.in_re, B, (size_t)k1->R, B, batch, (size_t)p1.in_bstride, (unsigned)k1->C, box_rows) ||
+                !encode_tile_map<T>(&p1.tmap_im, p1.in_im, B, (size_t)k1->R, B, batch, (size_t)p1.in_bstride, (unsigned)k1->C, box_rows))
+                return fail(PHASTFT_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+        }
         PipeCtl ctl;
         ctl.ticket = reinterpret_cast<unsigned*>(pl.pipe_state);
         ctl.done1 = reinterpret_cast<unsigned*>(pl.pipe_state + 64);
@@ -1141,8 +1164,12 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
                 prm.out_interleaved = il;
             }
             if (pass_events && done == 0 && p == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
-            const bool tma_mid = P == 3 && p == 1 && pl.pass[1].kt != nullptr && il == 1 && nb == 1;
-            int32_t st = launch_pass(pl, p, prm, nb, stream, 0, -1, tma || tma_mid);
+            bool tma3 = false;
+            if (P == 3 && pl.pass[p].kt != nullptr && il == 1 && nb == 1) {
+                if (p == 0) tma3 = io.in_il == 0 && ((reinterpret_cast<uintptr_t>(prm.in_re) | reinterpret_cast<uintptr_t>(prm.in_im)) & 15) == 0;
+                else tma3 = true;
+            }
+            int32_t st = launch_pass(pl, p, prm, nb, stream, 0, -1, tma || tma3);
             if (st) return st;
             if (pass_events && done == 0) CUDA_TRY(cudaEventRecord(pass_events[p + 1], stream));
         }

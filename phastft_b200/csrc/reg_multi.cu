@@ -42,12 +42,14 @@ ClusterEntry<T> make_cluster() {
     return e;
 }
 
-template <typename T, class RL1, int C1, int NT1, int V1, class RL2, int C2, int NT2, int V2, int MINB>
+template <typename T, class RL1, int C1, int NT1, int V1, class RL2, int C2, int NT2, int V2, int MINB, int ASYNC = 0>
 PipeEntry<T> make_pipe() {
-    using PK1 = PassKernel<T, RL1, C1, NT1, KIND_COL, 0, V1>;
-    using PK2 = PassKernel<T, RL2, C2, NT2, KIND_TRANS, 0, V2>;
+    using PK1 = PassKernel<T, RL1, C1, NT1, KIND_COL, ASYNC ? MODE_TMA_IN : MODE_PLAIN, V1>;
+    using PK2 = PassKernel<T, RL2, C2, NT2, KIND_TRANS, ASYNC ? MODE_BULK_IN : MODE_PLAIN, V2>;
     constexpr int NTF = NT1 > NT2 ? NT1 : NT2;
+    static_assert(!ASYNC || NT1 == NT2, "asynchronous bodies: thread 0 issues the copies, every thread is a worker");
     PipeEntry<T> e;
+    e.mode = ASYNC;
     e.R1 = RL1::R(); e.C1 = C1; e.NT1 = NT1; e.R2 = RL2::R(); e.C2 = C2; e.NT2 = NT2;
     e.rad1 = radix_string<RL1>(); e.rad2 = radix_string<RL2>();
     e.fn = reinterpret_cast<const void*>(&fft_pipe2_kernel<PK1, PK2, T, NTF, MINB>);
@@ -114,6 +116,8 @@ const std::vector<PipeEntry<PHAST_T>>& pipe_registry<PHAST_T>() {
         v.push_back(make_pipe<T, R512, CN, 256, 3, R512, CN, 256, 3, M512>());       // 2^18
         v.push_back(make_pipe<T, R1024, CN, NT1024, 0, R512, CN, 256, 3, M1024>());  // 2^19 = {10,9}
         v.push_back(make_pipe<T, R1024, CN, NT1024, 0, R1024, CN, NT1024, 0, M1024>());  // 2^20
+        // the same 2^16 pair with asynchronous tile input (both stages a single trip: NT = 16 * C)
+        v.push_back(make_pipe<T, R256, CN, 16 * CN, 0, R256, CN, 16 * CN, 0, M256, 1>());
         (void)M64; (void)CH;
         return v;
     }();

@@ -61,6 +61,9 @@ void add_strided_kernels<PHAST_T, PHAST_KIND>(std::vector<KernelEntry<PHAST_T>>&
     v.push_back(make_entry_async<T, KIND, CN, 32 * CN, MODE, 0, 1, 301, 32, 32>());      // 1024 rows, 128 KB tile
     v.push_back(make_entry_async<T, KIND, CH, 32 * CH, MODE, 0, 3, 300, 16, 32>());      // 512 rows, 32 KB tile
     v.push_back(make_entry_async<T, KIND, CN, 32 * CN, MODE, 0, 1, 301, 16, 32>());      // 512 rows, 64 KB tile
+    // the 256-row end passes of 3-pass plans (128-byte runs) and the batch tiles (64-byte runs), one task per thread per stage
+    v.push_back(make_entry_async<T, KIND, CW, 16 * CW, MODE, 0, 0, 300, 16, 16>());      // 256 rows x CW
+    v.push_back(make_entry_async<T, KIND, CN, 16 * CN, MODE, 0, 0, 300, 16, 16>());      // 256 rows x CN
 }
 
 }  // namespace phast

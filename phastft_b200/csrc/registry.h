@@ -35,6 +35,7 @@ struct ClusterEntry {
 // Matched to a plan by the descriptors of its two pass kernels.
 template <typename T>
 struct PipeEntry {
+    int mode = 0;          // 0: plain pass bodies; 1: asynchronous tile input (TMA boxes of the planar input / bulk rows of the ring)
     int R1, C1, NT1, R2, C2, NT2;
     std::string rad1, rad2;
     const void* fn;

@@ -211,8 +211,8 @@ def test_tma_path_in_a_stream_of_calls():
 # ---- pipelined two-pass launch: one grid runs both passes, intermediates in an L2-resident ring of workspace slots ----
 @pytest.mark.parametrize("dt,log_n,batch", [(np.float32, 16, 300), (np.float64, 16, 70), (np.float64, 14, 1100), (np.float32, 14, 700),
                                             (np.float64, 18, 20), (np.float32, 20, 9)])
-@pytest.mark.parametrize("ring_mb", [1, 32])
-def test_pipelined_launch_is_bit_identical_to_two_launches(dt, log_n, batch, ring_mb, monkeypatch):
+@pytest.mark.parametrize("ring_mb,tma", [(1, 0), (32, 0), (1, 1), (32, 1)])
+def test_pipelined_launch_is_bit_identical_to_two_launches(dt, log_n, batch, ring_mb, tma, monkeypatch):
     """fft_pipe2_kernel runs the same two pass bodies as the two-launch plan (same kernels, same tables), so the results must be
     bit-identical; a 1 MiB ring forces many wrap-arounds of the workspace slots (the pass-1 tiles then really wait for pass 2 to
     drain their slot, and pass 2 discards its input lines from L2), 32 MiB is the default."""
@@ -228,8 +228,13 @@ def test_pipelined_launch_is_bit_identical_to_two_launches(dt, log_n, batch, rin
     pf.fft_dit_batch(a_re, a_im, pf.Direction.Forward, plain, batch)
     monkeypatch.setenv("PHASTFT_PIPE", "1")
     monkeypatch.setenv("PHASTFT_PIPE_RING_MB", str(ring_mb))
+    monkeypatch.setenv("PHASTFT_PIPE_TMA", str(tma))        # the 2^16 pairs also exist with TMA / bulk tile input; other sizes fall back
     piped = planner_cls(dt)(n, 0)
     assert "one pipelined launch" in piped.describe(), piped.describe()
+    if tma and log_n != 16:
+        pytest.skip("no asynchronous pair for this size")
+    if tma:
+        assert "TMA / bulk tile input" in piped.describe(), piped.describe()
     b_re = torch.from_numpy(re_h).cuda(); b_im = torch.from_numpy(im_h).cuda()
     before = pf.launch_count()
     pf.fft_dit_batch(b_re, b_im, pf.Direction.Forward, piped, batch)
@@ -258,8 +263,9 @@ def test_tma_middle_pass_of_three_pass_plans(dt, log_n, monkeypatch):
     a_re, a_im = re0.clone(), im0.clone()
     fft(a_re, a_im, pf.Direction.Forward, plain)
     monkeypatch.setenv("PHASTFT_TMA_MID", "1")
+    monkeypatch.setenv("PHASTFT_TMA_ENDS", "1")         # and the 256-row end passes: planar TMA boxes in, bulk rows of the workspace in
     tma = planner_cls(dt)(n, 0)
-    assert "middle pass by TMA" in tma.describe(), tma.describe()
+    assert "middle pass by TMA" in tma.describe() and "end passes by TMA" in tma.describe(), tma.describe()
     b_re, b_im = re0.clone(), im0.clone()
     fft(b_re, b_im, pf.Direction.Forward, tma)
     scale = float(torch.maximum(a_re.abs().max(), a_im.abs().max()))
