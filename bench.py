@@ -242,7 +242,7 @@ def workload_config(workload: str, gpus: int):
 # ------------------------------------------------------------------------------------------------
 def traffic_table():
     """Measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu captures)."""
-    for name in ("r02_traffic.json", "traffic.json"):
+    for name in ("r02_traffic.json", "r01_traffic.json"):
         f = ROOT / "profiles" / name
         if f.exists():
             try:

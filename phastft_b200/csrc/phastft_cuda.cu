@@ -1822,7 +1822,7 @@ int32_t oneshot_r2c_plan(OneShotCache<PlanR2c<T>>& c, size_t n, int device, Plan
 extern "C" {
 
 const char* phastft_last_error(void) { return g_last_error.c_str(); }
-const char* phastft_version(void) { return "phastft_cuda 0.1.0 (sm_100a)"; }
+const char* phastft_version(void) { return "phastft_cuda 0.2.0 (sm_100a)"; }
 int32_t phastft_host_register(void* host_ptr, size_t bytes) {
     if (!host_ptr || !bytes) return fail(PHASTFT_ERR_INVALID_ARG, "NULL or empty range");
     CUDA_TRY(cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
