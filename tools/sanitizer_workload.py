@@ -57,4 +57,49 @@ z = (rng.uniform(-1, 1, 1 << 15) + 1j * rng.uniform(-1, 1, 1 << 15)).astype(np.c
 ref = np.fft.ifft(z)
 pf.fft_64_interleaved(z, pf.Direction.Reverse)
 assert np.max(np.abs(z - ref)) / np.max(np.abs(ref)) < 1e-13
+# ---- round 2: thread-block-cluster launch (DSMEM exchange), TMA / bulk tile input, pipelined two-pass launch, 128 KB one-CTA kernels ----
+def batch_check(dt, n, b, tolv):
+    P = pf.PlannerDit64 if dt == np.float64 else pf.PlannerDit32
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    pl = P(n)
+    d_re = torch.rand(n * b, dtype=tdt, device="cuda"); d_im = torch.rand(n * b, dtype=tdt, device="cuda")
+    x = (d_re.cpu().numpy().astype(np.float64) + 1j * d_im.cpu().numpy()).reshape(b, n)
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, pl, b)
+    got = (d_re.cpu().numpy().astype(np.float64) + 1j * d_im.cpu().numpy()).reshape(b, n)
+    ref = np.fft.fft(x, axis=1)
+    assert np.max(np.abs(got - ref)) / np.max(np.abs(ref)) < tolv, (dt, n, b, pl.describe())
+    return pl.describe()
+
+
+os.environ["PHASTFT_CLUSTER"] = "1"
+os.environ["PHASTFT_ONE_CTA_MAX"] = "14"
+for dt, sizes in ((np.float64, (13, 14, 15, 16)), (np.float32, (14, 15, 16))):
+    for ln in sizes:
+        d = batch_check(dt, 1 << ln, 19, 1e-13 if dt == np.float64 else 1e-5)
+        assert "CLUSTER" in d or "batches: ROW" in d, d
+os.environ.pop("PHASTFT_CLUSTER"); os.environ.pop("PHASTFT_ONE_CTA_MAX")
+os.environ["PHASTFT_PIPE"] = "1"; os.environ["PHASTFT_PIPE_RING_MB"] = "1"
+for tma in ("0", "1"):
+    os.environ["PHASTFT_PIPE_TMA"] = tma
+    for dt, n, b in ((np.float32, 1 << 16, 70), (np.float64, 1 << 16, 40), (np.float64, 1 << 14, 300)):
+        assert "pipelined" in batch_check(dt, n, b, 1e-13 if dt == np.float64 else 1e-5)
+for k in ("PHASTFT_PIPE", "PHASTFT_PIPE_RING_MB", "PHASTFT_PIPE_TMA"):
+    os.environ.pop(k)
+os.environ["PHASTFT_TMA"] = "1"
+for dt, f, P in ((np.float64, pf.fft_64_dit_with_planner, pf.PlannerDit64), (np.float32, pf.fft_32_dit_with_planner, pf.PlannerDit32)):
+    for n in (1 << 18, 1 << 20):
+        re = rng.uniform(-1, 1, n).astype(dt); im = rng.uniform(-1, 1, n).astype(dt)
+        ref = np.fft.fft(re.astype(np.float64) + 1j * im)
+        pl = P(n)
+        assert ",tma" in pl.describe()
+        f(re, im, pf.Direction.Forward, pl)
+        assert np.max(np.abs(re + 1j * im - ref)) / np.max(np.abs(ref)) < (1e-13 if dt == np.float64 else 1e-5)
+os.environ.pop("PHASTFT_TMA")
+n = 1 << 25          # middle pass by TMA (the default for 2^25+)
+re = rng.uniform(-1, 1, n); im = rng.uniform(-1, 1, n)
+ref0 = np.sum(re) + 1j * np.sum(im)
+pl = pf.PlannerDit64(n)
+assert "middle pass by TMA" in pl.describe()
+pf.fft_64_dit_with_planner(re, im, pf.Direction.Forward, pl)
+assert abs(re[0] + 1j * im[0] - ref0) < 1e-6
 print("sanitizer workload ok")
