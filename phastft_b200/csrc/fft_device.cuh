@@ -361,6 +361,15 @@ template <int... Rs> struct RadixList {
     }
 };
 
+// Offset (in complex elements) of stage s's [i][m] twiddle table inside the concatenation used by the one-CTA kernels:
+// stage q (1 <= q < S) owns L_q = Ns(q) * rad(q) entries.
+template <class RL>
+__host__ __device__ constexpr int tw_im_offset(int s) {
+    int off = 0;
+    for (int q = 1; q < s; ++q) off += RL::Ns(q) * RL::rad(q);
+    return off;
+}
+
 // Digit reversal of the tail index for stage 1:  mp = n_2*(M/r_2) + n_3*(M/(r_2 r_3)) + ... + n_S
 //   ->  j = n_2 + r_2*n_3 + r_2*r_3*n_4 + ...        (M = R / r_1)
 template <class RL>

@@ -56,6 +56,8 @@ struct PassParams {
     int tw_shift;                  // exponent scale: e_N = e_L << tw_shift   (N / L)
     Tw2 tw2;                       // two-level W_N table
     const cx<T>* __restrict__ tw_stage;  // W_R^e, e < R           (stage twiddles)
+    const cx<T>* __restrict__ tw_stage_im;  // KIND_ROW: per stage s >= 1 the table [i][m] = W_L^(m*i), L = Ns(s)*rad(s), concatenated
+                                         // (lanes run along m in a one-CTA kernel: consecutive lanes read consecutive entries)
     const cx<T>* __restrict__ tw_wc;     // KIND_TRANS, 2-pass plans: W_L^(c*m), [c][m] layout
     T scale;                       // multiplied into the stored result (1/N for the inverse)
     // cluster exchange (XCH = 1 producer only): the consuming pass's tile is [CB rows][P2 points]
@@ -291,6 +293,14 @@ struct PassKernel {
                 const cx<T> ws[8] = {w1, w1, w2, w3, w4, w5, w6, w7};
 #pragma unroll
                 for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], ws[i]);
+            } else if constexpr (KIND == KIND_ROW) {
+                // One-CTA kernels run their lanes along the row, so m differs from lane to lane: W_R^(m*i) out of the plain W_R table is
+                // a 32-way gather (15 of them per radix-16 task: measured 40-50 % of these kernels' time, profiles/r02_tuning.md section 7).
+                // The per-stage table in [i][m] order makes every one of those loads a contiguous run.
+                constexpr int TW_OFF = tw_im_offset<RL>(s);
+                const cx<T>* tws = p.tw_stage_im + TW_OFF + m;
+#pragma unroll
+                for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], __ldg(tws + i * NS));
             } else {
 #pragma unroll
                 for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], __ldg(p.tw_stage + ((m * i) << TW_SHIFT)));

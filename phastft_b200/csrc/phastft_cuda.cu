@@ -186,6 +186,8 @@ struct PassDesc {
     const KernelEntry<T>* kb = nullptr;   // kernel when the call carries many transforms (multi-wave grids)
     const KernelEntry<T>* kt = nullptr;   // 2-pass plans of lone transforms: the pass with an asynchronous (TMA) tile input
     size_t tw_wc_off_t = (size_t)-1;      // W_L^(c*m) table for `kt`
+    size_t tw_im_off = (size_t)-1;        // one-CTA kernels: the per-stage [i][m] stage-twiddle tables for `k` ...
+    size_t tw_im_off_b = (size_t)-1;      // ... and for `kb`
     int log2R = 0, log2A = 0, log2B = 0, log2R1 = 0, log2Rprev = 0, has_tw = 0, tw_shift = 0;
     size_t tw_stage_off = 0;  // byte offsets into the table blob
     size_t tw_wc_off = (size_t)-1;
@@ -407,6 +409,14 @@ const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
     return dflt;
 }
 
+// Entries of the concatenated per-stage [i][m] stage-twiddle tables of a one-CTA kernel (stage q >= 1 owns Ns(q) * rad(q)).
+template <typename T>
+size_t tw_im_entries(const KernelEntry<T>* k) {
+    size_t tot = 0, ns = (size_t)k->rads[0];
+    for (int q = 1; q < k->stages; ++q) { tot += ns * (size_t)k->rads[q]; ns *= (size_t)k->rads[q]; }
+    return tot;
+}
+
 template <typename T>
 int32_t build_plan(size_t n, int device, Plan<T>** out) {
     if (!out) return fail(PHASTFT_ERR_INVALID_ARG, "out == NULL");
@@ -468,6 +478,16 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             d.tw_shift = ln - (f[p - 1] + f[p] + d.log2B);
         }
         d.tw_stage_off = off; off += (size_t(1) << f[p]) * sizeof(cx<T>);
+        if (kind == KIND_ROW) {
+            off = (off + 255) & ~size_t(255);
+            d.tw_im_off = off; off += std::max<size_t>(1, tw_im_entries<T>(d.k)) * sizeof(cx<T>);
+            if (d.kb && d.kb != d.k) {
+                off = (off + 255) & ~size_t(255);
+                d.tw_im_off_b = off; off += std::max<size_t>(1, tw_im_entries<T>(d.kb)) * sizeof(cx<T>);
+            } else {
+                d.tw_im_off_b = d.tw_im_off;
+            }
+        }
         if (kind == KIND_TRANS && pl->num_passes == 2) {
             d.tw_wc_off = off;
             off += (size_t)d.k->C * ((size_t(1) << f[p]) / d.k->first_radix) * sizeof(cx<T>);
@@ -533,6 +553,8 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         if (d.k) {
             d.tw_stage_off = off; off += (size_t(1) << ln) * sizeof(cx<T>);
             off = (off + 255) & ~size_t(255);
+            d.tw_im_off = d.tw_im_off_b = off; off += std::max<size_t>(1, tw_im_entries<T>(d.k)) * sizeof(cx<T>);
+            off = (off + 255) & ~size_t(255);
             pl->alt_row_min_batch = ln <= 12 ? 4 : 32;
         }
     }
@@ -581,6 +603,23 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             double re, im;
             root_of_unity(e, R, re, im);
             tw[e].x = (T)re; tw[e].y = (T)im;
+        }
+        for (int which = 0; which < 2; ++which) {      // one-CTA kernels: per-stage [i][m] tables, W_L^(m*i) with L = Ns * rad
+            const KernelEntry<T>* kk = which ? d.kb : d.k;
+            const size_t ioff = which ? d.tw_im_off_b : d.tw_im_off;
+            if (!kk || kk->kind != KIND_ROW || ioff == (size_t)-1 || (which && ioff == d.tw_im_off)) continue;
+            cx<T>* t = reinterpret_cast<cx<T>*>(pl->blob_host.data() + ioff);
+            size_t ns = (size_t)kk->rads[0];
+            for (int q = 1; q < kk->stages; ++q) {
+                const size_t rad = (size_t)kk->rads[q], L = ns * rad;
+                for (size_t i = 0; i < rad; ++i)
+                    for (size_t m = 0; m < ns; ++m) {
+                        double re, im;
+                        root_of_unity((uint64_t)(m * i), L, re, im);
+                        t[i * ns + m].x = (T)re; t[i * ns + m].y = (T)im;
+                    }
+                t += L; ns = L;
+            }
         }
         for (int which = 0; which < 3; ++which) {
             const KernelEntry<T>* kk = which == 2 ? d.kt : which ? d.kb : d.k;
@@ -836,6 +875,8 @@ int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const 
     prm.tw2.lo_bits = pl.lo_bits;
     prm.tw_stage = reinterpret_cast<const cx<T>*>(pl.blob_dev + d.tw_stage_off);
     const size_t wc_off = use_kt ? d.tw_wc_off_t : many ? d.tw_wc_off_b : d.tw_wc_off;
+    const size_t im_off = many ? d.tw_im_off_b : d.tw_im_off;
+    prm.tw_stage_im = im_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + im_off);
     prm.tw_wc = wc_off == (size_t)-1 ? nullptr : reinterpret_cast<const cx<T>*>(pl.blob_dev + wc_off);
     unsigned long long blocks;
     prm.blk_offset = 0; prm.kt_base = 0; prm.log2_ktn = d.log2R1 - ilog2(k->C);

@@ -16,6 +16,7 @@ template <typename T>
 struct KernelEntry {
     int kind, R, C, NT, first_radix, stages, variant;
     int mode = 0;          // MODE_PLAIN, or MODE_TMA_IN / MODE_BULK_IN (asynchronous tile input)
+    int rads[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // the stage radices (the planner builds the one-CTA kernels' [i][m] stage-twiddle tables from them)
     size_t smem;
     const void* fn;        // fft_pass_kernel<...>; NULL for the passes of a cluster launch (they only exist inside it)
     std::string radices;
@@ -63,6 +64,7 @@ KernelEntry<T> make_entry_v() {
     static_assert(PK::SMEM_BYTES <= 227 * 1024, "tile exceeds the 227 KB shared memory of an sm_100 CTA");
     KernelEntry<T> e;
     e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.variant = ID;
+    for (int q = 0; q < RL::S && q < 8; ++q) e.rads[q] = RL::rad(q);
     e.smem = PK::SMEM_BYTES;
     e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, VARIANT, MINB>);
     e.radices = radix_string<RL>();
