@@ -299,8 +299,17 @@ struct PassKernel {
                 // The per-stage table in [i][m] order makes every one of those loads a contiguous run.
                 constexpr int TW_OFF = tw_im_offset<RL>(s);
                 const cx<T>* tws = p.tw_stage_im + TW_OFF + m;
+                // only the rows i = 1, 2, 4, 8, ... are loaded; W^(m*i) for the other i is the product of two earlier ones
+                // (i = hi + lo, hi the top bit: at most popcount(i) - 1 <= 3 products deep for radix 16): 4 loads + 11 products
+                // instead of 15 loads per radix-16 task
+                cx<T> w[RAD];
 #pragma unroll
-                for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], __ldg(tws + i * NS));
+                for (int i = 1; i < RAD; ++i) {
+                    const int hi = 1 << (31 - __builtin_clz((unsigned)i));
+                    if (i == hi) w[i] = __ldg(tws + i * NS);
+                    else w[i] = ctwid<T>(w[hi], w[i - hi]);
+                    x[i] = ctwid<T>(x[i], w[i]);
+                }
             } else {
 #pragma unroll
                 for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], __ldg(p.tw_stage + ((m * i) << TW_SHIFT)));
