@@ -6,10 +6,12 @@ import time, and if no CUDA device is present every call returns PHASTFT_ERR_NO_
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libphastft_cuda.so"
+# PHASTFT_LIB: load another build of the same library (tools/experiments/build_variant.py); still no fallback.
+LIB_PATH = Path(os.environ["PHASTFT_LIB"]) if os.environ.get("PHASTFT_LIB") else _PKG / "libphastft_cuda.so"
 
 OK = 0
 ERR_NO_DEVICE = 102

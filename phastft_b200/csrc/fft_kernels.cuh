@@ -23,6 +23,9 @@
 //              digit-reversing transpose, written as C-element contiguous runs.
 //   KIND_ROW   whole transform in one CTA (N <= 4096 f64 / 8192 f32): rows contiguous in and out.
 #pragma once
+#ifndef PHAST_EXP_STAGE_TW
+#define PHAST_EXP_STAGE_TW 0
+#endif
 #include <cuda.h>
 #include <type_traits>
 
@@ -311,8 +314,23 @@ struct PassKernel {
                     x[i] = ctwid<T>(x[i], w[i]);
                 }
             } else {
+#if PHAST_EXP_STAGE_TW == 1      // experiment: no stage twiddles (wrong results; prices them: profiles/r02_exp_tw_pass.txt)
+#elif PHAST_EXP_STAGE_TW == 2    // experiment: the round-1 form, one table load per twiddle
 #pragma unroll
                 for (int i = 1; i < RAD; ++i) x[i] = ctwid<T>(x[i], __ldg(p.tw_stage + ((m * i) << TW_SHIFT)));
+#else
+                // Lanes run along c here, so a warp holds 32 / C distinct m: each W_R^(m*i) load is a 2...8-way gather with a
+                // stride that grows with i.  Loads for i = 1, 2, 4, ... only, the others by products as above: 2-6 % of the
+                // whole transform (2^26 f64 1082 -> 1025 us; without any stage twiddles it would be 993).
+                cx<T> w[RAD];
+#pragma unroll
+                for (int i = 1; i < RAD; ++i) {
+                    const int hi = 1 << (31 - __builtin_clz((unsigned)i));
+                    if (i == hi) w[i] = __ldg(p.tw_stage + ((m * i) << TW_SHIFT));
+                    else w[i] = ctwid<T>(w[hi], w[i - hi]);
+                    x[i] = ctwid<T>(x[i], w[i]);
+                }
+#endif
             }
             DftC<T, RAD>::run(x);
             if constexpr (!LAST) {
