@@ -69,6 +69,11 @@ struct PassParams {
     // ring of workspace slots (fft_pipe2_kernel): transform b's intermediate lives in slot b % ring (ring a power of two; 0 = none)
     int out_ring;                  // KIND_COL: applied to the batch index of the OUTPUT address
     int in_ring;                   // KIND_TRANS: applied to the batch index of the INPUT address
+    // c2r pre-processing on load (MODE_C2R_IN only): in_re / in_im are the N/2 + 1 bins of the half-spectrum, the pass's
+    // input element k is built from bins k and N/2 - k with the twiddle W_N^k out of this table
+    Tw2 pre_tw2;
+    int pre_log2half;              // log2(N/2); 0 = no pre-processing
+    double2 pre_wc[32];            // W_(2 R1)^i, i < R1 = the kernel's first radix
     // TMA tile input (MODE_TMA_IN only): one tensor map per planar array, dims {B columns, R rows, batch}
     alignas(64) CUtensorMap tmap_re;
     alignas(64) CUtensorMap tmap_im;
@@ -169,7 +174,10 @@ __device__ __forceinline__ void bulk_load_1d(unsigned smem_dst, const void* gsrc
 //      CTAs share an SM); the threads wait on the mbarrier, read their stage-1 inputs out of the landing zone, and go on as usual
 //   4  bulk tile input (KIND_TRANS, interleaved intermediates): the tile's C rows are contiguous in the workspace -- C
 //      cp.async.bulk copies land them as [c][t], then as mode 2
-enum { MODE_PLAIN = 0, MODE_XCH_PRODUCE = 1, MODE_XCH_CONSUME = 2, MODE_TMA_IN = 3, MODE_BULK_IN = 4 };
+//   5  c2r pre-processing on load (first pass of the half-length inverse transform inside c2r): the input element k is
+//      computed from bins k and N/2 - k of the half-spectrum while it is being loaded (the reference's separate sweep
+//      r2c.rs:764-780 and its scratch round trip disappear: one HBM pass less per c2r)
+enum { MODE_PLAIN = 0, MODE_XCH_PRODUCE = 1, MODE_XCH_CONSUME = 2, MODE_TMA_IN = 3, MODE_BULK_IN = 4, MODE_C2R_IN = 5 };
 template <typename T, class RL, int C, int NT, int KIND, int XCH = 0, int VARIANT = 0>
 struct PassKernel {
     static constexpr int S = RL::S;
@@ -220,9 +228,47 @@ struct PassKernel {
     // predicates both layouts into one stream (every launch then issues the other layout's dead loads and
     // selects, and the selects of the interleaved path split its loads into two dependent batches).
     // Layout class: 0 planar, 1 interleaved (re, im), 2 interleaved swapped (im, re), -1 = test at run time.
+    // MODE_C2R_IN: element k of the half-length inverse transform's input, built on the fly from the half-spectrum
+    // (same arithmetic, in the same order, as c2r_preprocess_kernel below; r2c.rs:263-347).  The inverse runs as a forward
+    // transform of the swapped parts (r2c.rs:782), so the kernel is handed (im, re).
+    template <int N>
+    static __device__ __forceinline__ void gload_c2r(const PassParams<T>& p, long long a0, long long step, cx<T> (&x)[N]) {
+        // element i is bin k = a0 + i * step with step = (N/2) / R1 (first pass: R * B = N/2), so its twiddle
+        // W_N^k = W_N^a0 * W_(2 R1)^i: one table lookup per task, the second factors are launch constants (pre_wc).
+        // Loads in groups of 8 (f64): 4 scalars per element, all of a group in flight at once.
+        const long long half = 1LL << p.pre_log2half;
+        const T* __restrict__ fr = p.in_re + a0;
+        const T* __restrict__ fi = p.in_im + a0;
+        const T* __restrict__ sr = p.in_re + (half - a0);
+        const T* __restrict__ si = p.in_im + (half - a0);
+        const double2 wb = p.pre_tw2.get((uint32_t)a0);
+        constexpr int G = (sizeof(T) == 8 && N > 8) ? 8 : N;
+#pragma unroll
+        for (int g0 = 0; g0 < N; g0 += G) {
+            T re_f[G], im_f[G], re_s[G], im_s[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const long long off = (long long)(g0 + i) * step;
+                re_f[i] = fr[off]; im_f[i] = fi[off];
+                re_s[i] = sr[-off]; im_s[i] = -si[-off];
+            }
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const double2 wd = (g0 + i == 0) ? wb : cmul_d(wb, p.pre_wc[g0 + i]);
+                const T c_h = T(0.5 * wd.x), s_h = T(0.5 * wd.y);
+                const T zx_re = T(0.5) * (re_f[i] + re_s[i]), zx_im = T(0.5) * (im_f[i] + im_s[i]);
+                const T dr = re_f[i] - re_s[i], di = im_f[i] - im_s[i];
+                const T zy_re = c_h * dr + s_h * di;
+                const T zy_im = c_h * di - s_h * dr;
+                x[g0 + i] = make_cx<T>(zx_im + zy_re, zx_re - zy_im);
+            }
+        }
+    }
     template <int N, int IL = -1>
     static __device__ __forceinline__ void gload_n(const PassParams<T>& p, long long a0, long long step, cx<T> (&x)[N]) {
-        if constexpr (IL < 0) {
+        if constexpr (XCH == MODE_C2R_IN) {
+            gload_c2r<N>(p, a0, step, x);
+        } else if constexpr (IL < 0) {
             if (p.in_interleaved == 0) gload_n<N, 0>(p, a0, step, x);
             else if (p.in_interleaved == 1) gload_n<N, 1>(p, a0, step, x);
             else gload_n<N, 2>(p, a0, step, x);
@@ -614,7 +660,7 @@ struct PassKernel {
                 }
             }
         };
-        if constexpr (PRELOAD) stage1(std::integral_constant<int, 0>{});
+        if constexpr (PRELOAD || XCH == MODE_C2R_IN) stage1(std::integral_constant<int, 0>{});
         else if (p.in_interleaved == 0) stage1(std::integral_constant<int, 0>{});
         else if (p.in_interleaved == 1) stage1(std::integral_constant<int, 1>{});
         else stage1(std::integral_constant<int, 2>{});

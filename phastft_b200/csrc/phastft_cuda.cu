@@ -185,6 +185,7 @@ struct PassDesc {
     const KernelEntry<T>* k = nullptr;    // kernel for a lone transform
     const KernelEntry<T>* kb = nullptr;   // kernel when the call carries many transforms (multi-wave grids)
     const KernelEntry<T>* kt = nullptr;   // 2-pass plans of lone transforms: the pass with an asynchronous (TMA) tile input
+    const KernelEntry<T>* kc = nullptr;   // first pass only: `k` with the c2r pre-processing folded into its loads (MODE_C2R_IN)
     size_t tw_wc_off_t = (size_t)-1;      // W_L^(c*m) table for `kt`
     size_t tw_im_off = (size_t)-1;        // one-CTA kernels: the per-stage [i][m] stage-twiddle tables for `k` ...
     size_t tw_im_off_b = (size_t)-1;      // ... and for `kb`
@@ -472,6 +473,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const bool wide_b = (p == 0 || last) && far_stride >= (size_t(64) << 10);
         d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b, false, 0, pref_c, pref_v);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
+        if (p == 0 && kind == KIND_COL)         // the same tile with the c2r pre-processing in its loads, if compiled (c2r_dev uses it)
+            for (const auto& e : registry<T>())
+                if (e.mode == MODE_C2R_IN && e.kind == kind && e.R == d.k->R && e.C == d.k->C && e.NT == d.k->NT &&
+                    e.variant == d.k->variant && e.rl == d.k->rl) d.kc = &e;
         if (p > 0) {
             d.has_tw = 1;
             d.log2Rprev = f[p - 1];
@@ -649,6 +654,8 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kb->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kb->smem));
         if (pl->pass[p].kt)
             CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kt->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kt->smem));
+        if (pl->pass[p].kc)
+            CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kc->smem));
     }
     if (pl->alt_row.k)
         CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.k->smem));
@@ -791,6 +798,11 @@ struct Io {
     T* out_re; T* out_im;
     long long in_bstride, out_bstride;
     int in_il, out_il;   // 0 planar, 1 interleaved, 2 interleaved with re/im swapped
+    // c2r: in_re / in_im are the half-spectrum's N/2 + 1 bins and the first pass builds its input from them while loading
+    // (PassDesc::kc); pre_log2half = log2(N/2), 0 = off
+    Tw2 pre_tw2 = {nullptr, nullptr, 0};
+    int pre_log2half = 0;
+    const double2* pre_wc = nullptr;     // host: W_(2 R1)^i, i < 32 (PlanR2c::pre_wc)
 };
 
 // k1_lo / k1_cnt (multi-pass plans, batch == 1): restrict a pass AFTER the first to the sub-transforms
@@ -866,6 +878,10 @@ int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const 
                           bool use_kt) {
     const bool many = !use_kt && d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
     const KernelEntry<T>* k = use_kt ? d.kt : many ? d.kb : d.k;
+    if (base.pre_log2half) {
+        if (p != 0 || use_kt || many || !d.kc) return fail(PHASTFT_ERR_INVALID_ARG, "c2r pre-processing on load: lone first pass with a MODE_C2R_IN kernel only");
+        k = d.kc;
+    }
     PassParams<T> prm = base;
     prm.batch = (int)batch;
     prm.log2A = d.log2A; prm.log2B = d.log2B; prm.log2R1 = d.log2R1; prm.log2Rprev = d.log2Rprev;
@@ -1045,7 +1061,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     const PipeEntry<T>* pipe = nullptr;
     if (pl.num_passes == 2 && !pass_events) {
         if (batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21)) pipe = pl.pipe_b;
-        else if (batch == 1 && io.in_il == 0 && io.out_il == 0) pipe = pl.pipe_1;
+        else if (batch == 1 && io.in_il == 0 && io.out_il == 0 && !io.pre_log2half) pipe = pl.pipe_1;
     }
     size_t ws_need = chunk;
     const size_t ring = pipe ? pipe_ring_transforms(pl, batch) : 0;
@@ -1144,6 +1160,8 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
             prm.in_re = io.in_re + (io.in_il ? 2 : 1) * b * io.in_bstride;
             prm.in_im = io.in_im ? io.in_im + b * io.in_bstride : nullptr;
             prm.in_bstride = io.in_bstride; prm.in_interleaved = io.in_il;
+            prm.pre_tw2 = io.pre_tw2; prm.pre_log2half = io.pre_log2half;
+                if (io.pre_wc) memcpy(prm.pre_wc, io.pre_wc, sizeof(prm.pre_wc));
             prm.out_re = pl.ws_re; prm.out_im = pl.ws_im; prm.out_bstride = (long long)pl.n;
             if (pass_events && b == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
             int32_t st = launch_pass(pl, 0, prm, 1, stream);
@@ -1176,7 +1194,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     }
     const bool many_call = batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
     // asynchronous-input kernels: planar 16-byte-aligned input whose batch stride keeps the alignment, interleaved intermediates
-    const bool tma = P == 2 && pl.pass[0].kt && pl.pass[1].kt && !many_call && io.in_il == 0 && pl.ws_il != 0 &&
+    const bool tma = P == 2 && pl.pass[0].kt && pl.pass[1].kt && !many_call && io.in_il == 0 && pl.ws_il != 0 && !io.pre_log2half &&
                      ((reinterpret_cast<uintptr_t>(io.in_re) | reinterpret_cast<uintptr_t>(io.in_im)) & 15) == 0 &&
                      (batch == 1 || ((size_t)io.in_bstride * sizeof(T)) % 16 == 0);
     const int il = tma ? 1 : pl.ws_il >= 0 ? pl.ws_il : ((P == 3 || many_call) ? 1 : 0);
@@ -1190,6 +1208,8 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
                 prm.in_im = io.in_im ? io.in_im + done * io.in_bstride : nullptr;
                 prm.in_bstride = io.in_bstride;
                 prm.in_interleaved = io.in_il;
+                prm.pre_tw2 = io.pre_tw2; prm.pre_log2half = io.pre_log2half;
+                if (io.pre_wc) memcpy(prm.pre_wc, io.pre_wc, sizeof(prm.pre_wc));
             } else {
                 prm.in_re = pl.ws_re; prm.in_im = pl.ws_im; prm.in_bstride = (long long)pl.n;
                 prm.in_interleaved = il;
@@ -1207,7 +1227,7 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
             if (pass_events && done == 0 && p == 0) CUDA_TRY(cudaEventRecord(pass_events[0], stream));
             bool tma3 = false;
             if (P == 3 && pl.pass[p].kt != nullptr && il == 1 && nb == 1) {
-                if (p == 0) tma3 = io.in_il == 0 && ((reinterpret_cast<uintptr_t>(prm.in_re) | reinterpret_cast<uintptr_t>(prm.in_im)) & 15) == 0;
+                if (p == 0) tma3 = io.in_il == 0 && !io.pre_log2half && ((reinterpret_cast<uintptr_t>(prm.in_re) | reinterpret_cast<uintptr_t>(prm.in_im)) & 15) == 0;
                 else tma3 = true;
             }
             int32_t st = launch_pass(pl, p, prm, nb, stream, 0, -1, tma || tma3);
@@ -1649,6 +1669,7 @@ struct PlanR2c {
     unsigned char* tw_dev = nullptr;   // two-level W_n table for the untangle / preprocess twiddles
     size_t hi_elems = 0, lo_elems = 0;
     int lo_bits = 0;
+    double2 pre_wc[32];                // W_(2 R1)^i for the fused c2r first pass (R1 = first radix of inner->pass[0].kc)
     mutable std::mutex mu;
     mutable std::mutex host_mu;        // held for a whole *_host call (lock order: host_mu, then mu)
     mutable T* d_real = nullptr;       // host-API staging: N reals
@@ -1688,6 +1709,11 @@ int32_t build_plan_r2c(size_t n, int device, PlanR2c<T>** out) {
     for (size_t l = 0; l < pl->lo_elems; ++l) root_of_unity(l, n, tab[pl->hi_elems + l].x, tab[pl->hi_elems + l].y);
     CUDA_TRY(cudaMalloc(&pl->tw_dev, tab.size() * sizeof(double2)));
     CUDA_TRY(cudaMemcpy(pl->tw_dev, tab.data(), tab.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    memset(pl->pre_wc, 0, sizeof(pl->pre_wc));
+    if (pl->inner->num_passes >= 2 && pl->inner->pass[0].kc) {
+        const uint64_t r1 = (uint64_t)pl->inner->pass[0].kc->first_radix;
+        for (uint64_t i = 0; i < r1 && i < 32; ++i) root_of_unity(i, 2 * r1, pl->pre_wc[i].x, pl->pre_wc[i].y);
+    }
     // c2r scratch for the allocating variants lives in the plan (r2c.rs:716-718 allocates per call)
     CUDA_TRY(cudaMalloc(&pl->d_scr_re, (n / 2) * sizeof(T)));
     CUDA_TRY(cudaMalloc(&pl->d_scr_im, (n / 2) * sizeof(T)));
@@ -1737,6 +1763,22 @@ int32_t c2r_dev(const PlanR2c<T>* pl, const T* d_ire, const T* d_iim, T* d_out, 
     if ((d_sre == nullptr) != (d_sim == nullptr)) return fail(PHASTFT_ERR_INVALID_ARG, "pass both scratch arrays or neither");
     DeviceGuard g(pl->device);
     const size_t half = pl->n / 2;
+    // Pre-processing (r2c.rs:764-780) folded into the loads of the inverse transform's first pass when the plan has that
+    // kernel: no scratch, one HBM round trip of N/2 complex values less.  PHASTFT_C2R_FUSE=0 keeps the separate sweep.
+    const char* fuse_e = getenv("PHASTFT_C2R_FUSE");
+    const bool fuse_env = fuse_e ? atoi(fuse_e) != 0 : true;
+    const Plan<T>& in = *pl->inner;
+    // Measured (profiles/r02_exp_c2r_fuse2.txt): 1.03-1.26x for f64 up to N = 2^20 and from 2^24, 1.04-1.23x for every f32 size;
+    // f64 2^21..2^23 (whole signal in L2, so the sweep's scratch round trip is cheap, and the 1024-row tile of 2^21 keeps only 8
+    // of its 32 loads per thread in flight) 0.96-0.99x: those keep the separate sweep unless PHASTFT_C2R_FUSE=1 is set.
+    const bool fuse_size = sizeof(T) == 4 || in.log2n < 20 || in.log2n > 22 || fuse_e != nullptr;
+    if (fuse_env && fuse_size && in.num_passes >= 2 && in.pass[0].kc && !(in.cl && in.cl_min_batch <= 1) && !in.pipe_1) {
+        Io<T> io;
+        io.in_re = d_ire; io.in_im = d_iim; io.in_il = 0; io.in_bstride = (long long)half;
+        io.pre_tw2 = r2c_tw2(pl); io.pre_log2half = ilog2(half); io.pre_wc = pl->pre_wc;
+        io.out_re = d_out; io.out_im = nullptr; io.out_il = 2; io.out_bstride = (long long)half;
+        return run_c2c(in, io, 1, T(1) / (T)half, stream);
+    }
     std::unique_lock<std::mutex> lock(pl->mu, std::defer_lock);
     bool own_scratch = false, capturing = false;
     if (!d_sre) {

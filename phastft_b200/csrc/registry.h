@@ -15,11 +15,12 @@ namespace phast {
 template <typename T>
 struct KernelEntry {
     int kind, R, C, NT, first_radix, stages, variant;
-    int mode = 0;          // MODE_PLAIN, or MODE_TMA_IN / MODE_BULK_IN (asynchronous tile input)
+    int mode = 0;          // MODE_PLAIN, MODE_TMA_IN / MODE_BULK_IN (asynchronous tile input) or MODE_C2R_IN (c2r pre-processing on load)
     int rads[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // the stage radices (the planner builds the one-CTA kernels' [i][m] stage-twiddle tables from them)
     size_t smem;
     const void* fn;        // fft_pass_kernel<...>; NULL for the passes of a cluster launch (they only exist inside it)
-    std::string radices;
+    std::string radices;   // for describe(): the radices plus the mode / variant tags
+    std::string rl;        // the radices alone ("16x16"): same tile, same tables
 };
 
 // Both passes of a 2-pass plan in ONE launch by a K-CTA thread-block cluster, intermediate exchanged through
@@ -67,7 +68,7 @@ KernelEntry<T> make_entry_v() {
     for (int q = 0; q < RL::S && q < 8; ++q) e.rads[q] = RL::rad(q);
     e.smem = PK::SMEM_BYTES;
     e.fn = reinterpret_cast<const void*>(&fft_pass_kernel<T, RL, C, NT, KIND, VARIANT, MINB>);
-    e.radices = radix_string<RL>();
+    e.radices = e.rl = radix_string<RL>();
     if (ID) e.radices += ",v" + std::to_string(ID);
     return e;
 }
@@ -83,9 +84,17 @@ KernelEntry<T> make_entry_async() {
     e.kind = KIND; e.R = RL::R(); e.C = C; e.NT = NT; e.first_radix = RL::rad(0); e.stages = RL::S; e.variant = ID; e.mode = MODE;
     e.smem = PK::SMEM_BYTES;
     e.fn = reinterpret_cast<const void*>(&fft_pass_async_kernel<T, RL, C, NT, KIND, MODE, VARIANT, MINB>);
-    e.radices = radix_string<RL>() + (MODE == MODE_TMA_IN ? ",tma" : ",bulk");
+    e.rl = radix_string<RL>();
+    e.radices = e.rl + (MODE == MODE_TMA_IN ? ",tma" : MODE == MODE_BULK_IN ? ",bulk" : ",c2r");
     if (ID) e.radices += ",v" + std::to_string(ID);
     return e;
+}
+
+// a default entry plus, for first-pass (COL) tiles, the same kernel with the c2r pre-processing folded into its loads
+template <typename T, int KIND, int C, int NT, int VARIANT, int MINB, int ID, int... Rs>
+void push_entry(std::vector<KernelEntry<T>>& v) {
+    v.push_back(make_entry_v<T, KIND, C, NT, VARIANT, MINB, ID, Rs...>());
+    if constexpr (KIND == KIND_COL) v.push_back(make_entry_async<T, KIND, C, NT, MODE_C2R_IN, VARIANT, MINB, ID, Rs...>());
 }
 
 template <typename T, int KIND, int C, int NT, int... Rs>

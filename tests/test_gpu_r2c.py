@@ -210,3 +210,38 @@ def test_config_r2c_2pow24_roundtrip_device():
     assert float((d_y - d_x).abs().max().item()) <= 1e-6          # r2c.rs:1184 bound (abs 1e-6 on unit-scale data)
     assert float((d_y - d_x).abs().max().item()) <= 1e-12
     assert torch.equal(d_x, torch.from_numpy(x).cuda())           # input not modified
+
+
+# --- c2r: the pre-processing sweep (r2c.rs:764-780) is folded into the loads of the inverse transform's first pass
+# (MODE_C2R_IN kernels); PHASTFT_C2R_FUSE=0 keeps the separate sweep + scratch.  Same arithmetic either way. ------------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("log_n", [12, 13, 14, 15, 17, 19, 20, 21, 22, 23, 24, 25])
+def test_c2r_preprocessing_on_load_matches_separate_sweep(dt, log_n, monkeypatch):
+    import torch
+    pf = _pf()
+    P, r2c, r2c_p, c2r, c2r_p, c2r_ps = api(dt)
+    n = 1 << log_n; half = n // 2
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    g = torch.Generator(device="cuda"); g.manual_seed(77 + log_n)
+    d_re = torch.rand(half + 1, dtype=tdt, device="cuda", generator=g) * 2 - 1
+    d_im = torch.rand(half + 1, dtype=tdt, device="cuda", generator=g) * 2 - 1
+    keep_re, keep_im = d_re.clone(), d_im.clone()
+    pl = P(n)
+    outs = []
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("PHASTFT_C2R_FUSE", fuse)
+        y = torch.empty(n, dtype=tdt, device="cuda")
+        c2r_p(d_re, d_im, y, pl)
+        outs.append(y)
+        assert torch.equal(d_re, keep_re) and torch.equal(d_im, keep_im)     # the spectrum is an input: never written
+    scale = float(outs[1].abs().max().item())
+    # (the fused load derives W_N^k as a product of a table entry and a launch constant: one more rounding than the sweep)
+    assert float((outs[0] - outs[1]).abs().max().item()) <= tol(dt, n) * scale
+    # and against numpy on a Hermitian-valid spectrum (DC and Nyquist real)
+    d_im[0] = 0; d_im[half] = 0
+    monkeypatch.setenv("PHASTFT_C2R_FUSE", "1")
+    y = torch.empty(n, dtype=tdt, device="cuda")
+    c2r_p(d_re, d_im, y, pl)
+    if log_n <= 22:
+        truth = np.fft.irfft(d_re.cpu().numpy().astype(np.float64) + 1j * d_im.cpu().numpy().astype(np.float64), n)
+        assert np.max(np.abs(y.cpu().numpy() - truth)) <= tol(dt, n) * max(np.max(np.abs(truth)), 1.0) * 4
