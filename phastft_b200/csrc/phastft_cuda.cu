@@ -390,18 +390,21 @@ const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
         for (const auto& e : registry<T>())
             if (e.kind == KIND_ROW && e.R == R && e.variant == want) return &e;
     }
-    // measured per size (profiles/r01_tune19*.txt, profiles/r01_tune29*.txt); 0 = the lone-transform kernel is also the best batch kernel
+    // measured per size, batches of 2^24 points, after the stage twiddles of these kernels became contiguous loads + products
+    // (profiles/r02_exp_row2.txt; round 1's choices: profiles/r01_tune19*.txt, r01_tune29*.txt); 0 = the lone-transform kernel is
+    // also the best batch kernel (f64 2^9 / 2^10: 82.7 / 83.1 us = 0.98-0.99 of the measured HBM peak)
     const bool f64 = sizeof(T) == 8;
     int want = 0;
     switch (R) {
         case 4: case 8: want = 80; break;
         case 16: want = f64 ? 80 : 81; break;
         case 256: want = 70; break;
-        case 512: case 1024: want = 81; break;
+        case 512: want = f64 ? 0 : 81; break;
+        case 1024: want = 0; break;
         case 2048: want = f64 ? 81 : 70; break;
-        case 4096: want = f64 ? 70 : 0; break;
+        case 4096: want = 70; break;
         case 8192: want = f64 ? 90 : 0; break;
-        case 16384: want = 90; break;
+        case 16384: want = 91; break;
         default: break;
     }
     if (!want) return dflt;
@@ -545,9 +548,10 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
     }
     // Batches of transforms that one CTA can hold (128 KB tile: 2^13 f64, 2^14 f32) use a one-CTA kernel: one launch,
     // one HBM round trip.  PHASTFT_ONE_CTA_MAX (log2) lowers the limit for re-tuning.
-    // 2^13 f64 / 2^14 f32 in one CTA (128 KB tile, one CTA per SM) measured slower than two passes of small tiles
-    // (205 vs 182 us and 159 vs 97 us per 2^24 points, profiles/r02_exp_cluster1.txt), so the default limit stays 2^12.
-    int one_cta_max = 12;
+    // 2^13 f64 / 2^13-2^14 f32 in one CTA (64-128 KB tile): slower than two passes of small tiles while the stage twiddles were
+    // gathers (205 vs 182 us and 159 vs 97 us per 2^24 points, profiles/r02_exp_cluster1.txt), faster since they are contiguous
+    // loads + products (f64 2^13 147 vs 172 us, f32 2^13 61 vs 95, f32 2^14 78 vs 94, profiles/r02_exp_row2.txt).
+    int one_cta_max = sizeof(T) == 8 ? 13 : 14;
     if (const char* env = getenv("PHASTFT_ONE_CTA_MAX")) one_cta_max = std::min(atoi(env), sizeof(T) == 8 ? 13 : 14);
     if (pl->num_passes >= 2 && ln <= one_cta_max) {
         PassDesc<T>& d = pl->alt_row;

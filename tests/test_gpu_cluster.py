@@ -52,8 +52,8 @@ def test_batched_single_pass_vs_oracle(dt, log_n, direction, monkeypatch):
     the lone-transform path (another radix split, so tolerance not bit equality), padding between members untouched."""
     import torch
     pf, O = _pf(), _O()
-    monkeypatch.setenv("PHASTFT_CLUSTER", "1")          # both mechanisms are opt-in (measured slower than two launches)
-    monkeypatch.setenv("PHASTFT_ONE_CTA_MAX", "14")
+    monkeypatch.setenv("PHASTFT_CLUSTER", "1")          # the cluster launch is opt-in (measured slower than two launches);
+    monkeypatch.setenv("PHASTFT_ONE_CTA_MAX", "14")     # the one-CTA kernels (2^13 f64, 2^13-2^14 f32) are the default for batches
     n, batch = 1 << log_n, 41
     stride = n + 24
     rng = np.random.default_rng(100 * log_n + batch)
