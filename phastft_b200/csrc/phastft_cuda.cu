@@ -304,10 +304,11 @@ std::vector<int> choose_factors(int n) {
             pos = end + 1;
         }
     }
-    // A lone transform is one CTA only while that beats two many-CTA passes (profiles/r01_tune17*.txt: f64 2^12
-    // 7.9 us in one CTA vs 4.9 us as {6,6}; f32 2^12 5.6 vs 5.9 us).  Batches of <= 2^12-point transforms
-    // always use the one-CTA kernel (Plan::alt_row): one launch, one HBM round trip.
-    const int single_max = sizeof(T) == 8 ? 10 : 12;
+    // A lone transform is one CTA only while that beats two many-CTA passes (profiles/r02_exp_lone_row.txt, after the stage
+    // twiddles of the one-CTA kernels became contiguous loads + products: f64 2^11 3.3 us in one CTA vs 4.1 us as {5,6}, 2^12 4.7 vs
+    // 4.5; f32 2^12 3.1 us, 2^13 5.0 vs 5.6 as {6,7}).  Batches of <= 2^13 (f64) / 2^14 (f32) points always use a one-CTA
+    // kernel (Plan::alt_row): one launch, one HBM round trip.
+    const int single_max = sizeof(T) == 8 ? 11 : 13;
     if (n <= single_max) return {n};
     // two passes while both tiles stay <= 1024 points long; the ends of a 3-pass plan are kept at
     // 2^8 so they can use 128-byte runs in a 64 KB tile, the middle pass takes the rest (<= 2^10)
@@ -407,9 +408,8 @@ const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
         case 16384: want = 91; break;
         default: break;
     }
-    if (!want) return dflt;
-    for (const auto& e : registry<T>())
-        if (e.kind == KIND_ROW && e.R == R && e.variant == want) return &e;
+    for (const auto& e : registry<T>())        // want == 0: the plain build (the lone-transform choice may be another variant)
+        if (e.kind == KIND_ROW && e.R == R && e.variant == want && e.mode == MODE_PLAIN) return &e;
     return dflt;
 }
 
@@ -468,7 +468,11 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const bool half_mid = il3 && p == 1 && f[p] == 10;
         // lone 2^11-point f32 transform in one CTA: 8x16x16 (3.7 us) beats 4x8x8x8 (4.4 us), profiles/r01_tune30*.txt
         const bool row2048_f32 = kind == KIND_ROW && f[p] == 11 && sizeof(T) == 4;
-        const int pref_c = half_mid ? TileC<T>::CH : 0, pref_v = half_mid ? 62 : row2048_f32 ? 70 : 0;
+        // round 2 (profiles/r02_exp_lone_row.txt): f64 2^11 8x16x16 3.3 us (4x8x8x8: 3.7); f32 2^12 16x16x16 3.1 us (8x8x8x8: 4.1);
+        // f32 2^13 16x16x32 5.0 us (16x8x8x8: 5.6)
+        const bool row_r16 = kind == KIND_ROW && ((f[p] == 11 && sizeof(T) == 8) || (f[p] == 12 && sizeof(T) == 4));
+        const bool row8192_f32 = kind == KIND_ROW && f[p] == 13 && sizeof(T) == 4;
+        const int pref_c = half_mid ? TileC<T>::CH : 0, pref_v = half_mid ? 62 : (row2048_f32 || row_r16) ? 70 : row8192_f32 ? 91 : 0;
         d.k = pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide, /*l2_resident=*/!big, /*rows_total=*/n >> f[p], pref_c, pref_v);
         // batched calls are multi-wave streams whatever N is: wide runs only where the rows of a tile are
         // far apart in memory (>= 64 KiB: first-pass loads, last-pass stores of large N), else 64-byte runs

@@ -97,9 +97,9 @@ def test_product_never_imports_the_oracle():
 
 def test_planner_factorization_host_logic(pf):
     """The pass decomposition is pure host logic: N = prod 2^f_i, every pass size has a kernel (2^1..2^10 for
-    the strided kinds, one CTA up to 2^10 f64 / 2^12 f32), at most three passes."""
+    the strided kinds, one CTA up to 2^11 f64 / 2^13 f32), at most three passes."""
     from phastft_b200 import _lib
-    for bits, single_max in ((64, 10), (32, 12)):
+    for bits, single_max in ((64, 11), (32, 13)):
         assert _lib.plan_factorization(1, bits) == []
         for ln in range(1, 31):
             f = _lib.plan_factorization(1 << ln, bits)

@@ -360,7 +360,7 @@ def test_tune_mode_correct_and_not_slower(dt, log_n):
 # --- the layout of the intermediates between passes is an internal choice: both must be right -------------
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
 @pytest.mark.parametrize("ws_il", ["0", "1"])
-@pytest.mark.parametrize("log_n", [13, 18, 20, 21, 22])
+@pytest.mark.parametrize("log_n", [14, 18, 20, 21, 22])
 def test_forced_intermediate_layout(dt, ws_il, log_n, monkeypatch):
     """PHASTFT_WS_IL=0|1 forces planar / interleaved-complex intermediates (default: interleaved for 3-pass plans
     and large batches).  Same tolerance either way, forward and reverse, single and batched."""
@@ -388,7 +388,7 @@ def test_forced_intermediate_layout(dt, ws_il, log_n, monkeypatch):
 
 # --- large batches of small transforms take their own one-CTA kernels (two-stage 4/8/16-point, 32x16, 32x32, ...) ---
 @pytest.mark.parametrize("dt", [np.float64, np.float32])
-@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 256, 512, 1024, 2048, 4096])
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 256, 512, 1024, 2048, 4096, 8192, 16384])
 def test_large_batch_of_small_transforms(dt, n):
     """batch * N >= 2^21 switches a plan to its batch kernels; a ragged batch count leaves a partly filled last CTA."""
     import torch
