@@ -317,6 +317,13 @@ std::vector<int> choose_factors(int n) {
     if (n <= 20) { int a = (n + 1) / 2; return {a, n - a}; }
     if (n <= 22) return {7, n - 14, 7};
     if (n <= 26) return {8, n - 16, 8};
+    // beyond 2^26 an end pass has to grow too: the 1024-row pass goes in the middle (its tile arrives by TMA at 0.84 of the peak), the
+    // smaller end first (256-row first pass with 128-byte runs): 2^27 as {8,10,9} 2323 us vs 2743 us as {9,9,9} (f64), 1282 vs 1461 (f32),
+    // profiles/r02_exp_mid_batch.txt
+    // (2^28: {8,10,10} 4856 / 2595 us against 5589 / 2908 as {9,10,9} and 5842 / 2993 as {10,9,9})
+    if (n == 27) return {8, 10, 9};
+    if (n == 28) return {8, 10, 10};
+    if (n == 29) return {9, 10, 10};
     int a = (n + 2) / 3, b = (n - a + 1) / 2;
     return {a, n - a - b, b};
 }
@@ -478,7 +485,13 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         // far apart in memory (>= 64 KiB: first-pass loads, last-pass stores of large N), else 64-byte runs
         const size_t far_stride = (kind == KIND_COL ? (size_t(1) << d.log2B) : (n >> f[p])) * sizeof(T);
         const bool wide_b = (p == 0 || last) && far_stride >= (size_t(64) << 10);
-        d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b, false, 0, pref_c, pref_v);
+        // f32 batches of 2^17..2^20 points: 32-byte-run tiles (more CTAs per SM) 115-122 us per 2^24 points vs 117-140 us with 64-byte
+        // runs (profiles/r02_exp_mid_batch.txt); f64 measured the other way round and keeps its 64-byte runs
+        // (the opt-in pipelined launch is compiled for the 64-byte-run pairs: whenever PHASTFT_PIPE is set, to 0 or 1, the batch
+        // kernels stay those, so that the two settings run the same pass kernels and can be compared bit for bit)
+        const bool pipe_on = getenv("PHASTFT_PIPE") != nullptr;
+        const int pref_c_b = (sizeof(T) == 4 && pl->num_passes == 2 && ln >= 17 && kind != KIND_ROW && !pipe_on) ? TileC<T>::CH : pref_c;
+        d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b, false, 0, pref_c_b, pref_v);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
         if (p == 0 && kind == KIND_COL)         // the same tile with the c2r pre-processing in its loads, if compiled (c2r_dev uses it)
             for (const auto& e : registry<T>())
