@@ -204,6 +204,8 @@ struct Plan {
     PassDesc<T> pass[MAX_PASSES];
     PassDesc<T> alt_row;               // multi-pass N that one CTA can hold (<= 128 KB): the one-CTA kernel, used for batches
     size_t alt_row_min_batch = 4;
+    bool tma_lone = false;             // 2-pass plans: lone transforms through the asynchronous-input pair pass[].kt (PHASTFT_TMA=1)
+    bool tma_batch = false;            // ... and batched calls (batch * N >= 2^21): the default where the pair exists (PHASTFT_TMA_BATCH=0 disables)
     const ClusterEntry<T>* cl = nullptr;   // both passes in ONE launch by a thread-block cluster (exchange through DSMEM)
     PassDesc<T> cl_pass[2];
     size_t cl_min_batch = 0;           // calls with at least this many transforms use the cluster launch
@@ -526,13 +528,22 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         }
         off = (off + 255) & ~size_t(255);
     }
-    // Lone transforms as two passes of asynchronous-input kernels (TMA boxes of the planar input into 64 KB tiles,
-    // interleaved intermediates, programmatic dependent launch): PHASTFT_TMA=0 disables, PHASTFT_TMA_VARIANT picks a build.
+    // Two-pass plans with both tiles of 256 / 512 / 1024 rows (2^16..2^20 points): a pair of asynchronous-input kernels (TMA boxes
+    // of the planar input into the first pass's tile, bulk copies of the interleaved workspace's rows into the second's).
+    //   batched calls (batch * N >= 2^21, multi-wave grids): the default -- f64 2^20 x 16 279 -> 199 us, 2^19 250 -> 203, 2^17
+    //   208 -> 182, 2^16 188 -> 168; f32 2^18 122 -> 103, 2^17 116 -> 96, 4096 x 2^16 1323 -> 1275 us (profiles/r02_exp_tma_batch.txt);
+    //   PHASTFT_TMA_BATCH=0 keeps the register-staged kernels
+    //   lone transforms (single-wave grids): equal or slower (profiles/r02_exp_tma1.txt), opt-in with PHASTFT_TMA=1
+    // PHASTFT_TMA_VARIANT picks a build (300: 64 KB tiles, 301: 128 KB tiles).
     if (pl->num_passes == 2) {
-        int enabled = 0, want = 300;      // measured equal-or-slower than the plain kernels (profiles/r02_exp_tma1.txt): opt-in
-        if (const char* env = getenv("PHASTFT_TMA")) enabled = atoi(env);
-        if (getenv("PHASTFT_TMA_VARIANT") && !getenv("PHASTFT_TMA")) enabled = 1;
+        int lone = 0, batch = 1, want = 300;
+        if (const char* env = getenv("PHASTFT_TMA")) lone = atoi(env);
+        if (const char* env = getenv("PHASTFT_TMA_BATCH")) batch = atoi(env);
+        else if (getenv("PHASTFT_PIPE")) batch = 0;    // A/B runs of the pipelined launch compare against the kernels it is built from
+        if (getenv("PHASTFT_TMA_VARIANT") && !getenv("PHASTFT_TMA")) lone = 1;
         if (const char* env = getenv("PHASTFT_TMA_VARIANT")) want = atoi(env);
+        const bool enabled = lone || batch;
+        pl->tma_lone = lone != 0; pl->tma_batch = batch != 0;
         const KernelEntry<T>* t0 = nullptr; const KernelEntry<T>* t1 = nullptr;
         if (enabled && tensor_map_encoder())
             for (const auto& e : registry<T>()) {
@@ -762,7 +773,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
                  std::to_string(k->C) + " NT=" + std::to_string(k->NT) + " smem=" + std::to_string(k->smem);
         }
         if (pl->num_passes == 2 && pl->pass[0].kt) {
-            s += " || lone planar: ";
+            s += pl->tma_lone && pl->tma_batch ? " || planar input: " : pl->tma_lone ? " || lone planar: " : " || batches, planar input: ";
             for (int p = 0; p < 2; ++p) {
                 const auto* k = pl->pass[p].kt;
                 s += std::string(p ? " | " : "") + kind_name(k->kind) + " R=" + std::to_string(k->R) + "(" + k->radices + ") C=" + std::to_string(k->C) +
@@ -1215,7 +1226,10 @@ int32_t run_c2c(const Plan<T>& pl, const Io<T>& io, size_t batch, T scale, cudaS
     }
     const bool many_call = batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
     // asynchronous-input kernels: planar 16-byte-aligned input whose batch stride keeps the alignment, interleaved intermediates
-    const bool tma = P == 2 && pl.pass[0].kt && pl.pass[1].kt && !many_call && io.in_il == 0 && pl.ws_il != 0 && !io.pre_log2half &&
+    // batches: from 32 MiB of signal per array (2^22 f64 / 2^23 f32 points) -- below that the grid is about one wave and the pair
+    // measures equal or up to 5 % slower (profiles/r02_exp_tma_batch.txt, last block)
+    const bool tma_many = many_call && pl.tma_batch && (batch << pl.log2n) * sizeof(T) >= (size_t(32) << 20);
+    const bool tma = P == 2 && pl.pass[0].kt && pl.pass[1].kt && (many_call ? tma_many : pl.tma_lone) && io.in_il == 0 && pl.ws_il != 0 && !io.pre_log2half &&
                      ((reinterpret_cast<uintptr_t>(io.in_re) | reinterpret_cast<uintptr_t>(io.in_im)) & 15) == 0 &&
                      (batch == 1 || ((size_t)io.in_bstride * sizeof(T)) % 16 == 0);
     const int il = tma ? 1 : pl.ws_il >= 0 ? pl.ws_il : ((P == 3 || many_call) ? 1 : 0);

@@ -172,6 +172,7 @@ def test_tma_tile_input_vs_oracle(dt, log_n, variant, monkeypatch):
     planner = planner_cls(dt)(n, 0)
     assert ",tma" in planner.describe() and ",bulk" in planner.describe(), planner.describe()
     monkeypatch.setenv("PHASTFT_TMA", "0")
+    monkeypatch.setenv("PHASTFT_TMA_BATCH", "0")
     plain = planner_cls(dt)(n, 0)
     assert ",tma" not in plain.describe()
     fft = pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
@@ -186,6 +187,44 @@ def test_tma_tile_input_vs_oracle(dt, log_n, variant, monkeypatch):
         O.fft_dit(o_re, o_im, od)
         assert rel_linf(a, b, o_re, o_im) <= tol(dt, n)
         assert rel_linf(a, b, c, d) <= tol(dt, n)
+
+
+# ---- the same pair is the DEFAULT for batched calls of 2^16..2^20-point transforms (from 32 MiB of signal per array) ----------
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("log_n,batch,pad", [(16, 160, 0), (17, 70, 8), (18, 40, 0), (19, 20, 24), (20, 9, 0), (16, 130, 3)])
+def test_batches_through_tma_pair_by_default(dt, log_n, batch, pad, monkeypatch):
+    """Batched call, default settings: the asynchronous-input pair runs (describe says so) unless the batch stride breaks the
+    16-byte alignment TMA needs (pad = 3: the register-staged kernels then).  Every 5th member against the oracle, all members
+    against PHASTFT_TMA_BATCH=0 within tolerance, the padding between members untouched, and the inverse restores the input."""
+    import torch
+    pf, O = _pf(), _O()
+    n = 1 << log_n
+    stride = n + pad
+    planner = planner_cls(dt)(n, 0)
+    assert "batches, planar input:" in planner.describe() and ",tma" in planner.describe(), planner.describe()
+    rng = np.random.default_rng(31 * log_n + batch)
+    re_h = rng.uniform(-1, 1, batch * stride).astype(dt); im_h = rng.uniform(-1, 1, batch * stride).astype(dt)
+    d_re = torch.from_numpy(re_h).cuda(); d_im = torch.from_numpy(im_h).cuda()
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, planner, batch, stride)
+    g_re, g_im = d_re.cpu().numpy(), d_im.cpu().numpy()
+    monkeypatch.setenv("PHASTFT_TMA_BATCH", "0")
+    plain = planner_cls(dt)(n, 0)
+    assert ",tma" not in plain.describe()
+    p_re = torch.from_numpy(re_h).cuda(); p_im = torch.from_numpy(im_h).cuda()
+    pf.fft_dit_batch(p_re, p_im, pf.Direction.Forward, plain, batch, stride)
+    q_re, q_im = p_re.cpu().numpy(), p_im.cpu().numpy()
+    for b in range(batch):
+        s = slice(b * stride, b * stride + n)
+        assert rel_linf(g_re[s], g_im[s], q_re[s], q_im[s]) <= tol(dt, n), b
+        if b % 5 == 0 or b == batch - 1:
+            o_re, o_im = re_h[s].copy(), im_h[s].copy()
+            O.fft_dit(o_re, o_im, O.FORWARD)
+            assert rel_linf(g_re[s], g_im[s], o_re, o_im) <= tol(dt, n), b
+        if pad:
+            t = slice(b * stride + n, (b + 1) * stride)
+            assert np.array_equal(g_re[t], re_h[t]) and np.array_equal(g_im[t], im_h[t])
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Reverse, planner, batch, stride)
+    assert float(np.max(np.abs(d_re.cpu().numpy() - re_h))) <= 8 * tol(dt, n)
 
 
 def test_tma_path_in_a_stream_of_calls():
