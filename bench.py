@@ -275,7 +275,11 @@ def roofline_block(wl, alg_bytes, ms_per_step, pass_ms_alone, hbm_peak, peak_src
         total_traffic = tr.get("total")
     elif isinstance(tr, (int, float)):
         total_traffic = tr
-    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+    note = None
+    if per_pass and any(e["frac"] > 1.0 for e in per_pass):
+        note = ("a per-pass fraction above 1 means that pass streams its bytes faster than the copy kernel behind the measured peak did "
+                "(the peak is a measured copy bandwidth, not the HBM3e pin rate); the whole-transform `frac` is the roofline figure")
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "note": note,
             "traffic": total_traffic, "traffic_source": (f"profiles/{tname}" if tname and tr is not None else None),
             "peak_source": peak_src, "algorithmic_bytes": alg_bytes, "units": units_note,
             "per_pass": per_pass, "per_pass_frac": [e["frac"] for e in per_pass] if per_pass else None,
