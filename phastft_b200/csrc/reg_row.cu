@@ -37,6 +37,8 @@ void add_row_kernels<PHAST_T>(std::vector<KernelEntry<PHAST_T>>& v) {
     v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 81, 32, 16>());
     v.push_back(make_entry_v<T, KIND_ROW, 2, 64, 0, 0, 81, 32, 32>());
     v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 81, 16, 16, 8>());
+    // (ids 82 / 83 -- the 16..128-point kernels with 2x / 4x the transforms per CTA -- measured equal within 2 %, profiles/r02_exp_tiny.txt,
+    // and are not compiled: those sizes are bound by the load / store INSTRUCTION rate, 128 bytes per f32 warp access, not by CTA count)
     // id 90: the largest transforms ONE CTA can hold (128 KB tile): 2^13 f64, 2^14 f32 -- for batches one HBM round trip
     // instead of two passes (the north star's "<= 2^14 points entirely in one block")
     if constexpr (sizeof(T) == 8) {
