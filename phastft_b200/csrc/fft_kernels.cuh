@@ -177,7 +177,12 @@ __device__ __forceinline__ void bulk_load_1d(unsigned smem_dst, const void* gsrc
 //   5  c2r pre-processing on load (first pass of the half-length inverse transform inside c2r): the input element k is
 //      computed from bins k and N/2 - k of the half-spectrum while it is being loaded (the reference's separate sweep
 //      r2c.rs:764-780 and its scratch round trip disappear: one HBM pass less per c2r)
-enum { MODE_PLAIN = 0, MODE_XCH_PRODUCE = 1, MODE_XCH_CONSUME = 2, MODE_TMA_IN = 3, MODE_BULK_IN = 4, MODE_C2R_IN = 5 };
+//   6  bulk tile input AND output (KIND_ROW, batches whose transforms lie back to back in planar arrays): the CTA's C transforms
+//      are one contiguous run per plane -- two cp.async.bulk copies bring them in (landing zone = the tile, planar [c][r]), the
+//      last stage writes its results into a second planar staging area and two cp.async.bulk copies take them out.  The
+//      per-lane 4/8-byte accesses of the plain kernel (128 bytes per f32 warp instruction, the bound of the 16..128-point
+//      batches) become two asynchronous copies per CTA.
+enum { MODE_PLAIN = 0, MODE_XCH_PRODUCE = 1, MODE_XCH_CONSUME = 2, MODE_TMA_IN = 3, MODE_BULK_IN = 4, MODE_C2R_IN = 5, MODE_ROW_BULK = 6 };
 template <typename T, class RL, int C, int NT, int KIND, int XCH = 0, int VARIANT = 0>
 struct PassKernel {
     static constexpr int S = RL::S;
@@ -191,15 +196,17 @@ struct PassKernel {
     // shared memory: tile (only if S >= 2) + Um[M] + G[C][R1]
     static constexpr int TILE_ELEMS = (S >= 2) ? R * C : 0;
     static constexpr int G_ELEMS = (KIND == KIND_TRANS) ? C * R1 : R1;
-    static constexpr bool ASYNC_IN = (XCH == MODE_TMA_IN || XCH == MODE_BULK_IN);
+    static constexpr bool ASYNC_IN = (XCH == MODE_TMA_IN || XCH == MODE_BULK_IN || XCH == MODE_ROW_BULK);
     static constexpr size_t TABLE_END = sizeof(cx<T>) * (size_t)(TILE_ELEMS + M + G_ELEMS);
     static constexpr size_t MBAR_OFF = (TABLE_END + 15) & ~size_t(15);
-    static constexpr size_t SMEM_BYTES = ASYNC_IN ? MBAR_OFF + 16 : TABLE_END;
+    static constexpr size_t OUT_OFF = (MBAR_OFF + 16 + 127) & ~size_t(127);      // MODE_ROW_BULK: planar output staging [2][C][R]
+    static constexpr size_t SMEM_BYTES = XCH == MODE_ROW_BULK ? OUT_OFF + sizeof(cx<T>) * (size_t)TILE_ELEMS : ASYNC_IN ? MBAR_OFF + 16 : TABLE_END;
     static_assert(XCH == 0 || S >= 2, "an exchanging pass needs a shared-memory tile");
     static_assert(XCH != 1 || KIND == KIND_COL, "the producer of a cluster exchange is a COL pass");
     static_assert(XCH != 2 || KIND == KIND_TRANS, "the consumer of a cluster exchange is a TRANS pass");
     static_assert(XCH != MODE_TMA_IN || (KIND == KIND_COL && C * sizeof(T) >= 16), "TMA tile input: COL pass, rows of >= 16 bytes");
     static_assert(XCH != MODE_BULK_IN || KIND == KIND_TRANS, "bulk tile input: TRANS pass");
+    static_assert(XCH != MODE_ROW_BULK || KIND == KIND_ROW, "bulk tile input and output: one-CTA kernels");
 
     // ---- global element access -------------------------------------------------------------
     static __device__ __forceinline__ void gload(const PassParams<T>& p, long long idx, T& re, T& im) {
@@ -402,6 +409,14 @@ struct PassKernel {
             } else {
                 // last stage: g == 0, natural-order outputs kr = m + k*NS
                 if (KIND == KIND_ROW && c >= tile_rows_valid) continue;
+                if constexpr (XCH == MODE_ROW_BULK) {
+                    // natural-order planar staging; the bulk copies at the end of body() take it out
+                    T* ore = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(tile) + OUT_OFF) + c * R + m;
+                    T* oim = ore + C * R;
+                    const T sc = p.scale;
+#pragma unroll
+                    for (int k = 0; k < RAD; ++k) { ore[k * NS] = x[k].x * sc; oim[k * NS] = x[k].y * sc; }
+                } else
                 if constexpr (KIND == KIND_ROW) gstore_n<RAD, OL>(p, out_base + (long long)c * p.out_bstride + m, (long long)NS, x);
                 else gstore_n<RAD, OL>(p, out_base + (long long)m * out_kstride + c, (long long)NS * out_kstride, x);
             }
@@ -502,7 +517,7 @@ struct PassKernel {
             if (tid == 0) {
                 mbar_init(mbar, 1);
                 if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-                mbar_expect_tx(mbar, (unsigned)(TILE_ELEMS * sizeof(cx<T>)));
+                mbar_expect_tx(mbar, XCH == MODE_ROW_BULK ? (unsigned)(2 * rows_valid * R * sizeof(T)) : (unsigned)(TILE_ELEMS * sizeof(cx<T>)));
                 const unsigned tile_s = (unsigned)__cvta_generic_to_shared(tile);
                 if constexpr (XCH == MODE_TMA_IN) {
                     // boxes of at most 256 rows.  Planar input: re plane [R][C] then im plane [R][C].  Interleaved input (the
@@ -522,6 +537,10 @@ struct PassKernel {
                             tma_load_3d(tile_s + (unsigned)((R + r0) * C * sizeof(T)), &p.tmap_im, col0, r0, bz, mbar);
                         }
                     }
+                } else if constexpr (XCH == MODE_ROW_BULK) {
+                    const unsigned bytes = (unsigned)(rows_valid * R * sizeof(T));
+                    bulk_load_1d(tile_s, p.in_re + in_base, bytes, mbar);
+                    bulk_load_1d(tile_s + (unsigned)(C * R * sizeof(T)), p.in_im + in_base, bytes, mbar);
                 } else {
                     const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in_re) + in_base;
 #pragma unroll
@@ -593,7 +612,17 @@ struct PassKernel {
             if (t < M * C) {
                 int c, mp;
                 if constexpr (KIND == KIND_COL) { c = t % C; mp = t / C; } else { mp = t % M; c = t / M; }
-                if constexpr (XCH == MODE_TMA_IN) {
+                if constexpr (XCH == MODE_ROW_BULK) {
+                    const T* re_pl = reinterpret_cast<const T*>(tile) + c * R + mp;
+                    const T* im_pl = re_pl + C * R;
+                    if (c < rows_valid) {
+#pragma unroll
+                        for (int i = 0; i < R1; ++i) pre[i] = make_cx<T>(re_pl[i * M], im_pl[i * M]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < R1; ++i) pre[i] = make_cx<T>(T(0), T(0));
+                    }
+                } else if constexpr (XCH == MODE_TMA_IN) {
                     if (p.in_interleaved) {
                         const cx<T>* src = tile + mp * C + c;
 #pragma unroll
@@ -666,6 +695,20 @@ struct PassKernel {
         else stage1(std::integral_constant<int, 2>{});
         // ---- stages 2..S -------------------------------------------------------------------------
         run_stages<1>(p, tile, out_base, out_kstride, rows_valid, tid);
+        if constexpr (XCH == MODE_ROW_BULK) {
+            // the staging area was written through the generic proxy: make it visible to the asynchronous proxy, then one thread
+            // copies the two planes out and waits until the copies have READ shared memory before the CTA may exit
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned stage_s = (unsigned)__cvta_generic_to_shared(smem_raw + OUT_OFF);
+                const unsigned bytes = (unsigned)(rows_valid * R * sizeof(T));
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out_re + out_base), "r"(stage_s), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.out_im + out_base), "r"(stage_s + (unsigned)(C * R * sizeof(T))), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        }
     }
 
 };

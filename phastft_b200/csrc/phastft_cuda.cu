@@ -186,6 +186,7 @@ struct PassDesc {
     const KernelEntry<T>* kb = nullptr;   // kernel when the call carries many transforms (multi-wave grids)
     const KernelEntry<T>* kt = nullptr;   // 2-pass plans of lone transforms: the pass with an asynchronous (TMA) tile input
     const KernelEntry<T>* kc = nullptr;   // first pass only: `k` with the c2r pre-processing folded into its loads (MODE_C2R_IN)
+    const KernelEntry<T>* kr = nullptr;   // one-CTA plans: `kb` with its tile moved in and out by cp.async.bulk (MODE_ROW_BULK)
     size_t tw_wc_off_t = (size_t)-1;      // W_L^(c*m) table for `kt`
     size_t tw_im_off = (size_t)-1;        // one-CTA kernels: the per-stage [i][m] stage-twiddle tables for `k` ...
     size_t tw_im_off_b = (size_t)-1;      // ... and for `kb`
@@ -422,6 +423,19 @@ const KernelEntry<T>* pick_row_batch_kernel(int R, const KernelEntry<T>* dflt) {
     return dflt;
 }
 
+// The MODE_ROW_BULK build of a one-CTA batch kernel (same radices, C and id; NT may differ), or NULL.  Opt-in (PHASTFT_ROW_BULK=1):
+// bit-identical and measured equal or slower at every size (profiles/r02_exp_row_bulk.txt: f32 2^5 82.9 vs 77.5 us per 2^24
+// points, f64 2^12 169 vs 93 with the doubled shared memory) -- these kernels are not bound by their per-lane global accesses.
+template <typename T>
+const KernelEntry<T>* find_row_bulk(const KernelEntry<T>* kb) {
+    if (!kb || kb->kind != KIND_ROW) return nullptr;
+    const char* env = getenv("PHASTFT_ROW_BULK");
+    if (!env || atoi(env) == 0) return nullptr;
+    for (const auto& e : registry<T>())
+        if (e.mode == MODE_ROW_BULK && e.kind == KIND_ROW && e.R == kb->R && e.C == kb->C && e.variant == kb->variant && e.rl == kb->rl) return &e;
+    return nullptr;
+}
+
 // Entries of the concatenated per-stage [i][m] stage-twiddle tables of a one-CTA kernel (stage q >= 1 owns Ns(q) * rad(q)).
 template <typename T>
 size_t tw_im_entries(const KernelEntry<T>* k) {
@@ -495,6 +509,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         const int pref_c_b = (sizeof(T) == 4 && pl->num_passes == 2 && ln >= 17 && kind != KIND_ROW && !pipe_on) ? TileC<T>::CH : pref_c;
         d.kb = (kind == KIND_ROW) ? pick_row_batch_kernel<T>(1 << f[p], d.k) : pick_kernel<T>(kind, 1 << f[p], max_c, p, /*hbm_strided=*/wide_b, false, 0, pref_c_b, pref_v);
         if (!d.k) return fail(PHASTFT_ERR_INVALID_ARG, "no kernel for pass size 2^" + std::to_string(f[p]) + " kind " + kind_name(kind));
+        if (kind == KIND_ROW) d.kr = find_row_bulk<T>(d.kb);
         if (p == 0 && kind == KIND_COL)         // the same tile with the c2r pre-processing in its loads, if compiled (c2r_dev uses it)
             for (const auto& e : registry<T>())
                 if (e.mode == MODE_C2R_IN && e.kind == kind && e.R == d.k->R && e.C == d.k->C && e.NT == d.k->NT &&
@@ -587,6 +602,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         d.k = pick_kernel<T>(KIND_ROW, 1 << ln, 1 << 30, 0, false);
         d.k = pick_row_batch_kernel<T>(1 << ln, d.k);            // alt_row is only ever used for batches
         d.kb = d.k;
+        d.kr = find_row_bulk<T>(d.kb);
         if (d.k) {
             d.tw_stage_off = off; off += (size_t(1) << ln) * sizeof(cx<T>);
             off = (off + 255) & ~size_t(255);
@@ -688,9 +704,13 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
             CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kt->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kt->smem));
         if (pl->pass[p].kc)
             CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kc->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kc->smem));
+        if (pl->pass[p].kr)
+            CUDA_TRY(cudaFuncSetAttribute(pl->pass[p].kr->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->pass[p].kr->smem));
     }
     if (pl->alt_row.k)
         CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.k->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.k->smem));
+    if (pl->alt_row.kr)
+        CUDA_TRY(cudaFuncSetAttribute(pl->alt_row.kr->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->alt_row.kr->smem));
     if (pl->cl) {
         // usable only if the device can co-schedule at least one cluster of this shape
         cudaError_t ce = cudaFuncSetAttribute(pl->cl->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->cl->smem);
@@ -800,6 +820,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         if (pl->pipe_b) s += std::string(" [batches: one pipelined launch, ") + (pl->pipe_b->mode ? "TMA / bulk tile input, " : "") + std::to_string(pl->pipe_grid_b) + " resident CTAs, L2 ring]";
         if (pl->pipe_1) s += " [lone: one pipelined launch, " + std::to_string(pl->pipe_grid_1) + " resident CTAs]";
         if (pl->alt_row.k) s += " || batches: ROW R=" + std::to_string(pl->alt_row.k->R) + "(" + pl->alt_row.k->radices + ")";
+        if ((pl->num_passes == 1 && pl->pass[0].kr) || pl->alt_row.kr) s += " [contiguous planar batches: tile in / out by cp.async.bulk]";
         if (pl->cl)
             s += " || batches >= " + std::to_string(pl->cl_min_batch) + ": CLUSTER K=" + std::to_string(pl->cl->K) + " NT=" + std::to_string(pl->cl->NT) +
                  " " + std::to_string(pl->cl->k1.R) + "(" + pl->cl->k1.radices + ") x " + std::to_string(pl->cl->k2.R) + "(" + pl->cl->k2.radices +
@@ -910,6 +931,12 @@ int32_t prepare_pass_desc(const Plan<T>& pl, const PassDesc<T>& d, int p, const 
                           bool use_kt) {
     const bool many = !use_kt && d.kb != nullptr && batch > 1 && (batch << pl.log2n) >= (size_t(1) << 21);
     const KernelEntry<T>* k = use_kt ? d.kt : many ? d.kb : d.k;
+    // one-CTA batch kernel with bulk tile input / output: planar arrays, transforms back to back, 16-byte-aligned planes
+    if (many && d.kr && k == d.kb && base.in_interleaved == 0 && base.out_interleaved == 0 && base.in_bstride == (long long)pl.n &&
+        base.out_bstride == (long long)pl.n &&
+        ((reinterpret_cast<uintptr_t>(base.in_re) | reinterpret_cast<uintptr_t>(base.in_im) | reinterpret_cast<uintptr_t>(base.out_re) |
+          reinterpret_cast<uintptr_t>(base.out_im)) & 15) == 0)
+        k = d.kr;
     if (base.pre_log2half) {
         if (p != 0 || use_kt || many || !d.kc) return fail(PHASTFT_ERR_INVALID_ARG, "c2r pre-processing on load: lone first pass with a MODE_C2R_IN kernel only");
         k = d.kc;

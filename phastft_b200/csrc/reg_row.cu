@@ -37,6 +37,27 @@ void add_row_kernels<PHAST_T>(std::vector<KernelEntry<PHAST_T>>& v) {
     v.push_back(make_entry_v<T, KIND_ROW, 2, 32, 0, 0, 81, 32, 16>());
     v.push_back(make_entry_v<T, KIND_ROW, 2, 64, 0, 0, 81, 32, 32>());
     v.push_back(make_entry_v<T, KIND_ROW, 1, 128, 0, 0, 81, 16, 16, 8>());
+    // MODE_ROW_BULK builds of the batch kernels (tile in and out by cp.async.bulk, for batches that lie back to back in planar
+    // arrays; opt-in, PHASTFT_ROW_BULK=1 -- bit-identical, measured equal or slower, profiles/r02_exp_row_bulk.txt): same radices / C / id as the kernel pick_row_batch_kernel chooses for that size, NT = stage-1 tasks per CTA where
+    // the plain kernel makes two trips (the landing zone is read in a single trip)
+    {
+        constexpr int M6 = MODE_ROW_BULK;
+        constexpr bool F64 = sizeof(T) == 8;
+        v.push_back(make_entry_async<T, KIND_ROW, 64, 128, M6, 0, 0, 80, 2, 2>());
+        v.push_back(make_entry_async<T, KIND_ROW, 64, 256, M6, 0, 0, 80, 2, 4>());
+        if constexpr (F64) v.push_back(make_entry_async<T, KIND_ROW, 32, 128, M6, 0, 0, 80, 4, 4>());
+        else v.push_back(make_entry_async<T, KIND_ROW, 16, 64, M6, 0, 0, 81, 4, 4>());
+        v.push_back(make_entry_async<T, KIND_ROW, 16, 128, M6, 0, 0, 0, 4, 8>());
+        v.push_back(make_entry_async<T, KIND_ROW, 8, 64, M6, 0, 0, 0, 8, 8>());
+        v.push_back(make_entry_async<T, KIND_ROW, 4, 64, M6, 0, 0, 0, 16, 8>());
+        v.push_back(make_entry_async<T, KIND_ROW, 2, 32, M6, 0, 0, 70, 16, 16>());
+        if constexpr (F64) v.push_back(make_entry_async<T, KIND_ROW, 1, 64, M6, 0, 0, 0, 8, 8, 8>());
+        else v.push_back(make_entry_async<T, KIND_ROW, 2, 32, M6, 0, 0, 81, 32, 16>());
+        v.push_back(make_entry_async<T, KIND_ROW, 1, 128, M6, 0, 0, 0, 16, 8, 8>());
+        if constexpr (F64) v.push_back(make_entry_async<T, KIND_ROW, 1, 128, M6, 0, 0, 81, 16, 16, 8>());
+        else v.push_back(make_entry_async<T, KIND_ROW, 1, 256, M6, 0, 0, 70, 8, 16, 16>());
+        v.push_back(make_entry_async<T, KIND_ROW, 1, 256, M6, 0, 0, 70, 16, 16, 16>());
+    }
     // (ids 82 / 83 -- the 16..128-point kernels with 2x / 4x the transforms per CTA -- measured equal within 2 %, profiles/r02_exp_tiny.txt,
     // and are not compiled: those sizes are bound by the load / store INSTRUCTION rate, 128 bytes per f32 warp access, not by CTA count)
     // id 90: the largest transforms ONE CTA can hold (128 KB tile): 2^13 f64, 2^14 f32 -- for batches one HBM round trip

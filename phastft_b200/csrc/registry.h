@@ -15,7 +15,8 @@ namespace phast {
 template <typename T>
 struct KernelEntry {
     int kind, R, C, NT, first_radix, stages, variant;
-    int mode = 0;          // MODE_PLAIN, MODE_TMA_IN / MODE_BULK_IN (asynchronous tile input) or MODE_C2R_IN (c2r pre-processing on load)
+    int mode = 0;          // MODE_PLAIN, MODE_TMA_IN / MODE_BULK_IN (asynchronous tile input), MODE_C2R_IN (c2r pre-processing on load)
+                           // or MODE_ROW_BULK (one-CTA batch kernel, tile in and out by cp.async.bulk)
     int rads[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // the stage radices (the planner builds the one-CTA kernels' [i][m] stage-twiddle tables from them)
     size_t smem;
     const void* fn;        // fft_pass_kernel<...>; NULL for the passes of a cluster launch (they only exist inside it)
@@ -85,7 +86,8 @@ KernelEntry<T> make_entry_async() {
     e.smem = PK::SMEM_BYTES;
     e.fn = reinterpret_cast<const void*>(&fft_pass_async_kernel<T, RL, C, NT, KIND, MODE, VARIANT, MINB>);
     e.rl = radix_string<RL>();
-    e.radices = e.rl + (MODE == MODE_TMA_IN ? ",tma" : MODE == MODE_BULK_IN ? ",bulk" : ",c2r");
+    e.radices = e.rl + (MODE == MODE_TMA_IN ? ",tma" : MODE == MODE_BULK_IN ? ",bulk" : MODE == MODE_C2R_IN ? ",c2r" : ",bulk-io");
+    for (int q = 0; q < RL::S && q < 8; ++q) e.rads[q] = RL::rad(q);
     if (ID) e.radices += ",v" + std::to_string(ID);
     return e;
 }

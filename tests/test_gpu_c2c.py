@@ -438,3 +438,41 @@ def test_oneshot_plan_cache():
     a = np.ones(8, np.float32); b = np.zeros(8, np.float32)
     pf.fft_32_dit(a, b, pf.Direction.Forward)
     assert a[0] == 8 and np.all(a[1:] == 0)
+
+
+# --- one-CTA batch kernels with the tile moved in and out by cp.async.bulk (MODE_ROW_BULK, opt-in: measured equal or slower) for
+# batches that lie back to back in 16-byte-aligned planar arrays; same arithmetic as the per-lane loads / stores: bit-identical -----
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096])
+def test_bulk_tile_io_for_contiguous_batches(dt, n, monkeypatch):
+    import torch
+    pf = _pf()
+    batch = (1 << 21) // n + 13                      # ragged: the last CTA holds fewer transforms than its tile
+    rng = np.random.default_rng(900 + n)
+    re_h = rng.uniform(-1, 1, batch * n).astype(dt); im_h = rng.uniform(-1, 1, batch * n).astype(dt)
+    monkeypatch.setenv("PHASTFT_ROW_BULK", "1")
+    bulk = planner_for(dt, n)
+    assert "cp.async.bulk" in bulk.describe(), bulk.describe()
+    monkeypatch.setenv("PHASTFT_ROW_BULK", "0")
+    plain = planner_for(dt, n)
+    assert "cp.async.bulk" not in plain.describe()
+    for direction in (pf.Direction.Forward, pf.Direction.Reverse):
+        guard = torch.full((64,), 7.0, dtype=torch.float64 if dt == np.float64 else torch.float32, device="cuda")
+        a_re = torch.cat([torch.from_numpy(re_h).cuda(), guard]); a_im = torch.cat([torch.from_numpy(im_h).cuda(), guard])
+        b_re = torch.from_numpy(re_h).cuda(); b_im = torch.from_numpy(im_h).cuda()
+        pf.fft_dit_batch(a_re[:batch * n], a_im[:batch * n], direction, bulk, batch)
+        pf.fft_dit_batch(b_re, b_im, direction, plain, batch)
+        assert torch.equal(a_re[:batch * n], b_re) and torch.equal(a_im[:batch * n], b_im)
+        assert bool((a_re[batch * n:] == 7.0).all()) and bool((a_im[batch * n:] == 7.0).all())       # nothing written past the batch
+    # against numpy, and a view that is only 8-byte aligned falls back to the per-lane kernels with the same result
+    want = np.fft.fft(re_h.astype(np.float64).reshape(batch, n) + 1j * im_h.astype(np.float64).reshape(batch, n), axis=-1)
+    c_re = torch.from_numpy(re_h).cuda(); c_im = torch.from_numpy(im_h).cuda()
+    pf.fft_dit_batch(c_re, c_im, pf.Direction.Forward, bulk, batch)
+    got = (c_re.cpu().numpy().astype(np.float64) + 1j * c_im.cpu().numpy().astype(np.float64)).reshape(batch, n)
+    assert float(np.max(np.abs(got - want)) / np.max(np.abs(want))) <= tol(dt, n)
+    off = 2 if dt == np.float32 else 1               # shift the planes by 8 bytes
+    pad = torch.zeros(off, dtype=c_re.dtype, device="cuda")
+    d_re = torch.cat([pad, torch.from_numpy(re_h).cuda()])[off:]; d_im = torch.cat([pad, torch.from_numpy(im_h).cuda()])[off:]
+    assert d_re.data_ptr() % 16 != 0
+    pf.fft_dit_batch(d_re, d_im, pf.Direction.Forward, bulk, batch)
+    assert torch.equal(d_re, c_re) and torch.equal(d_im, c_im)
