@@ -410,7 +410,7 @@ def measure_batch(c, K, W, with_e2e=True):
         for r in range(c.world):
             rlo, rhi = c.shard_range(total, r, c.world)
             idx += [rlo + k for k in sorted({0, 1, rhi - rlo - 2, rhi - rlo - 1} & set(range(rhi - rlo)))]
-        slots = max(32, len(idx))                                      # >= 2^21 points: the call takes the batched kernels, like the shards
+        slots = max(128, len(idx))                                     # >= 32 MiB per array: the call takes the same kernels as the shards (TMA pair)
         chk_re = torch.zeros(slots * n, dtype=torch.float32, device=c.dev); chk_im = torch.zeros_like(chk_re)
         for j, k in enumerate(idx):
             chk_re[j * n:(j + 1) * n] = full_re[k * n:(k + 1) * n]; chk_im[j * n:(j + 1) * n] = full_im[k * n:(k + 1) * n]
