@@ -582,6 +582,7 @@ int32_t build_plan(size_t n, int device, Plan<T>** out) {
         if (const char* env = getenv("PHASTFT_TMA_ENDS")) ends = atoi(env);
         if (tensor_map_encoder())
             for (const auto& e : registry<T>()) {
+                if (enabled >= 2 && e.variant == 310 && e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.R == (1 << f[1]) && e.C == TileC<T>::CH) pl->pass[1].kt = &e;
                 if (e.variant != 300) continue;
                 if (enabled && e.mode == MODE_TMA_IN && e.kind == KIND_COL && e.R == (1 << f[1]) && e.C == TileC<T>::CH) pl->pass[1].kt = &e;
                 // the 128-byte-run end passes: planar boxes in (first pass), contiguous rows of the workspace in (last pass)

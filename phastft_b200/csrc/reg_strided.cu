@@ -63,6 +63,11 @@ void add_strided_kernels<PHAST_T, PHAST_KIND>(std::vector<KernelEntry<PHAST_T>>&
     v.push_back(make_entry_async<T, KIND, CN, 32 * CN, MODE, 0, 1, 301, 32, 32>());      // 1024 rows, 128 KB tile
     v.push_back(make_entry_async<T, KIND, CH, 32 * CH, MODE, 0, 3, 300, 16, 32>());      // 512 rows, 32 KB tile
     v.push_back(make_entry_async<T, KIND, CN, 32 * CN, MODE, 0, 1, 301, 16, 32>());      // 512 rows, 64 KB tile
+    // half-width 256- and 128-row tiles: the middle pass of the 3-pass plans of 2^21..2^24 points (COL only)
+    if constexpr (KIND == KIND_COL) {
+        v.push_back(make_entry_async<T, KIND, CH, 16 * CH, MODE, 0, 0, 310, 16, 16>());  // 256 rows x CH   (id 310: middle passes only,
+        v.push_back(make_entry_async<T, KIND, CH, 8 * CH, MODE, 0, 0, 310, 16, 8>());    // 128 rows x CH    never half of a 2-pass pair)
+    }
     // the 256-row end passes of 3-pass plans (128-byte runs) and the batch tiles (64-byte runs), one task per thread per stage
     v.push_back(make_entry_async<T, KIND, CW, 16 * CW, MODE, 0, 0, 300, 16, 16>());      // 256 rows x CW
     v.push_back(make_entry_async<T, KIND, CN, 16 * CN, MODE, 0, 0, 300, 16, 16>());      // 256 rows x CN
