@@ -316,3 +316,35 @@ def test_tma_middle_pass_of_three_pass_plans(dt, log_n, monkeypatch):
     assert abs(e_out - e_in) / e_in <= 64 * eps * np.log2(n)
     fft(b_re, b_im, pf.Direction.Reverse, tma)
     assert max(float((b_re - re0).abs().max()), float((b_im - im0).abs().max())) <= (1e-10 if dt == np.float64 else 3e-5)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("log_n", [21, 22, 23, 24])
+def test_tma_middle_pass_of_the_smaller_three_pass_plans(dt, log_n, monkeypatch):
+    """PHASTFT_TMA_MID=2 (opt-in): the 128- / 256-row middle passes of 2^21..2^24 through the half-width id-310 TMA tiles.  Same
+    stages and tables as the plain middle pass; checked against numpy (2^21, 2^22) and against the default plan within tolerance,
+    and the inverse restores the input."""
+    import torch
+    pf = _pf()
+    n = 1 << log_n
+    tdt = torch.float64 if dt == np.float64 else torch.float32
+    g = torch.Generator(device="cuda"); g.manual_seed(1000 + log_n)
+    re0 = torch.rand(n, dtype=tdt, device="cuda", generator=g) * 2 - 1; im0 = torch.rand(n, dtype=tdt, device="cuda", generator=g) * 2 - 1
+    fft = pf.fft_64_dit_with_planner if dt == np.float64 else pf.fft_32_dit_with_planner
+    plain = planner_cls(dt)(n, 0)
+    assert "middle pass by TMA" not in plain.describe()
+    a_re, a_im = re0.clone(), im0.clone()
+    fft(a_re, a_im, pf.Direction.Forward, plain)
+    monkeypatch.setenv("PHASTFT_TMA_MID", "2")
+    tma = planner_cls(dt)(n, 0)
+    assert "middle pass by TMA" in tma.describe() and "v310" in tma.describe(), tma.describe()
+    b_re, b_im = re0.clone(), im0.clone()
+    fft(b_re, b_im, pf.Direction.Forward, tma)
+    scale = float(torch.maximum(a_re.abs().max(), a_im.abs().max()))
+    assert max(float((a_re - b_re).abs().max()), float((a_im - b_im).abs().max())) / scale <= tol(dt, n)
+    if log_n <= 22:
+        want = np.fft.fft(re0.cpu().numpy().astype(np.float64) + 1j * im0.cpu().numpy().astype(np.float64))
+        got = b_re.cpu().numpy().astype(np.float64) + 1j * b_im.cpu().numpy().astype(np.float64)
+        assert float(np.max(np.abs(got - want)) / np.max(np.abs(want))) <= tol(dt, n)
+    fft(b_re, b_im, pf.Direction.Reverse, tma)
+    assert max(float((b_re - re0).abs().max()), float((b_im - im0).abs().max())) <= (1e-10 if dt == np.float64 else 3e-5)
